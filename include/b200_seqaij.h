@@ -1,0 +1,169 @@
+/*
+ * b200_seqaij.h -- C ABI of the Blackwell-native (sm_100a) SeqAIJ sparse mat-vec hot path.
+ *
+ * This is the drop-in boundary underneath PETSc's per-type operator table: the five C symbols the
+ * reference (olcf/PETSC-OpenACC) substitutes at link time --
+ *     MatMult_SeqAIJ        src/openacc-step3/MatMult_SeqAIJ.patch:12
+ *     MatAssemblyEnd_SeqAIJ src/openacc-step2/MatAssemblyEnd_SeqAIJ.patch:12
+ *     MatDestroy_SeqAIJ     src/openacc-step2/MatDestroy_SeqAIJ.patch:12
+ * plus MatMultAdd_SeqAIJ / MatMultTranspose_SeqAIJ (PETSc 3.7.6 aij.c, named by the north star) --
+ * are thin shims over the functions below (see include/b200_petsc_symbols.h and INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; PetscInt = int32_t, PetscScalar = MatScalar = double
+ *     (scripts/petsc-release.sh:6,62 and no --with-64-bit-indices);
+ *   - every function returns 0 on success or a non-zero b200 error code (never aborts), mirroring
+ *     PetscErrorCode propagation (src/openacc-step1/MatMult_SeqAIJ.patch:16);
+ *   - "h_" pointers are host memory, "d_" pointers are device memory of the current device;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute entry returns
+ *     B200_ERR_NO_DEVICE.
+ */
+#ifndef B200_SEQAIJ_H
+#define B200_SEQAIJ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------------------------- */
+enum {
+  B200_OK             = 0,
+  B200_ERR_ARG        = 60,  /* bad argument (PETSC_ERR_ARG_* range is 56..63 in PETSc)        */
+  B200_ERR_NO_DEVICE  = 92,  /* no CUDA device / not sm_100 (PETSC_ERR_LIB-like)               */
+  B200_ERR_CUDA       = 76,  /* a CUDA runtime call failed; see b200_last_error()              */
+  B200_ERR_MEM        = 55,  /* allocation failed (PETSC_ERR_MEM)                              */
+  B200_ERR_STATE      = 73,  /* object in wrong state (PETSC_ERR_ARG_WRONGSTATE)               */
+  B200_ERR_TIMEOUT    = 77   /* a peer flag was not seen within the spin budget (halo)         */
+};
+
+/* ---- summation-order modes ---------------------------------------------------------------- */
+/* The reference sums each row strictly left to right (PetscSparseDensePlusDot,
+ * src/openacc-step1/MatMult_SeqAIJ.patch:30).
+ *   EXACT      one accumulator per row, left to right, multiply and add rounded separately
+ *              (bit-exact against the oracle built with -ffp-contract=off);
+ *   EXACT_FMA  same order with a fused multiply-add (bit-exact against the oracle's *_fma);
+ *   FAST       kernel picked from the row-length histogram; rows may be summed by several lanes
+ *              (|y - y_ref| <= 1e-13 * sum_j |a_ij x_j| per row).                              */
+enum { B200_MODE_FAST = 0, B200_MODE_EXACT = 1, B200_MODE_EXACT_FMA = 2 };
+
+/* Kernel override for tests and sweeps (AUTO = choose from the histogram). */
+enum {
+  B200_KERNEL_AUTO   = 0,
+  B200_KERNEL_ROW    = 1,  /* thread per row straight from global memory (the reference's shape) */
+  B200_KERNEL_STREAM = 2,  /* TMA-bulk-staged CSR tiles, thread per row out of shared memory     */
+  B200_KERNEL_VECTOR = 3,  /* sub-warp per row, __shfl_xor reduction                             */
+  B200_KERNEL_MERGE  = 4,  /* nnz-balanced merge-path tiles with carry fix-up                    */
+  B200_KERNEL_CPROW  = 5   /* compressed-row: only the non-empty rows                            */
+};
+
+typedef struct b200_csr_s *b200_csr_t;
+
+typedef struct {
+  int32_t m, n, nz;
+  int32_t nonzerorowcnt;     /* rows with at least one entry (a->nonzerorowcnt)                 */
+  int32_t rmax;              /* longest row (a->rmax)                                           */
+  int32_t compressedrow_use; /* MatCheckCompressedRow verdict, ratio 0.6                        */
+  int32_t cprow_nrows;
+  int32_t kernel_fast;       /* B200_KERNEL_* chosen for MODE_FAST                              */
+  int32_t kernel_exact;      /* B200_KERNEL_* chosen for MODE_EXACT*                            */
+  int32_t vector_lanes;      /* lanes per row of the VECTOR kernel                              */
+  int32_t stream_tiles;      /* number of tiles of the STREAM kernel (0 = not applicable)       */
+  int32_t merge_tiles;
+  int32_t has_transpose;     /* explicit transpose copy is resident                             */
+  int32_t hist[16];          /* row-length histogram: [0],[1],[2],[3-4],[5-8],...,[>16384]      */
+  uint64_t device_bytes;     /* HBM held by this handle                                         */
+} b200_csr_info_t;
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+int         b200_init(int device);           /* cudaSetDevice + capability check (sm_100)       */
+const char *b200_last_error(void);           /* text of the last failure on this thread         */
+uint64_t    b200_launch_count(void);         /* kernels of this library launched so far         */
+int         b200_device_sm_count(void);
+const char *b200_version(void);
+
+/* ---- CSR residency (replaces the OpenACC enter/exit data directives,
+ *      src/openacc-step2/MatMult_SeqAIJ.patch:19-21, MatAssemblyEnd...:28-29,42-44,
+ *      MatDestroy...:26-34) ---------------------------------------------------------------- */
+/* Mirror host CSR (a->i, a->j, a->a) once into device-resident, 128-bit aligned arrays and
+ * build the per-matrix kernel plan (row histogram, tile tables, compressed-row index).       */
+int b200_csr_create(b200_csr_t *out, int32_t m, int32_t n, const int32_t *h_ai,
+                    const int32_t *h_aj, const double *h_aa);
+/* Same from arrays that already live on the device (copied; the caller keeps ownership).     */
+int b200_csr_create_from_device(b200_csr_t *out, int32_t m, int32_t n, const int32_t *d_ai,
+                                const int32_t *d_aj, const double *d_aa);
+/* Values changed, pattern did not (MatAssemblyEnd after MatSetValues into existing slots,
+ * MatZeroRowsColumns, MatScale ...): re-upload aa only.                                      */
+int b200_csr_update_values(b200_csr_t A, const double *h_aa);
+int b200_csr_destroy(b200_csr_t A);
+int b200_csr_get_info(b200_csr_t A, b200_csr_info_t *info);
+int b200_csr_set_kernel(b200_csr_t A, int kernel); /* B200_KERNEL_* override, AUTO resets     */
+/* Build (or drop) the explicit transpose used by the deterministic MatMultTranspose.         */
+int b200_csr_build_transpose(b200_csr_t A);
+/* Device pointers of the mirrors (for tests / composition), any may be NULL.                 */
+int b200_csr_device_arrays(b200_csr_t A, const int32_t **d_ai, const int32_t **d_aj,
+                           const double **d_aa);
+
+/* ---- the hot path, device-resident vectors ------------------------------------------------ */
+/* y = A x                      MatMult_SeqAIJ                                                 */
+int b200_spmv(b200_csr_t A, const double *d_x, double *d_y, int mode, void *stream);
+/* z = y + A x (z may alias y)  MatMultAdd_SeqAIJ                                              */
+int b200_spmv_add(b200_csr_t A, const double *d_x, const double *d_y, double *d_z, int mode,
+                  void *stream);
+/* y = A^T x                    MatMultTranspose_SeqAIJ                                        */
+int b200_spmv_transpose(b200_csr_t A, const double *d_x, double *d_y, int mode, void *stream);
+/* y = z + A^T x                MatMultTransposeAdd_SeqAIJ                                     */
+int b200_spmv_transpose_add(b200_csr_t A, const double *d_x, const double *d_z, double *d_y,
+                            int mode, void *stream);
+
+/* ---- the hot path, HOST vectors (what MatMult_SeqAIJ(Mat,Vec,Vec) sees in PETSc 3.7.6) ----
+ * x is uploaded, y downloaded, synchronous on return (the reference ends with `acc wait`,
+ * src/openacc-step4/MatMult_SeqAIJ.patch:91).  Row-blocked and pipelined over three streams
+ * like the reference's step 4 (:51-72) when the matrix is banded.                             */
+int b200_spmv_host(b200_csr_t A, const double *h_x, double *h_y, int mode);
+int b200_spmv_add_host(b200_csr_t A, const double *h_x, const double *h_y, double *h_z, int mode);
+int b200_spmv_transpose_host(b200_csr_t A, const double *h_x, double *h_y, int mode);
+/* Pinned host allocation for Vec arrays (page-locked memory makes the copies above async).   */
+int b200_host_alloc(void **p, size_t bytes);
+int b200_host_free(void *p);
+int b200_host_register(void *p, size_t bytes);
+int b200_host_unregister(void *p);
+
+/* ---- CG vector kernels (KSPSolve_CG's VecDot/VecNorm/VecAXPY/VecAYPX, fused) -------------- */
+/* Results of reductions are written to device memory (d_out) so a solve never syncs the host
+ * unless asked to.  All reductions are deterministic (fixed grid, fixed tree).               */
+int b200_vec_set(double *d_x, double a, int64_t n, void *stream);
+int b200_vec_copy(double *d_y, const double *d_x, int64_t n, void *stream);
+int b200_vec_axpy(double *d_y, double a, const double *d_x, int64_t n, void *stream);   /* y+=a x */
+int b200_vec_aypx(double *d_y, double a, const double *d_x, int64_t n, void *stream);   /* y=x+a y */
+int b200_vec_pointwise_mult(double *d_w, const double *d_x, const double *d_y, int64_t n,
+                            void *stream);
+int b200_vec_dot(const double *d_x, const double *d_y, int64_t n, double *d_out, void *stream);
+int b200_vec_norm2(const double *d_x, int64_t n, double *d_out, void *stream);
+int b200_vec_norm_inf(const double *d_x, int64_t n, double *d_out, void *stream);
+int b200_vec_sum(const double *d_x, int64_t n, double *d_out, void *stream);
+
+/* PETSc-free CG (KSPCG semantics: left-preconditioned, preconditioned-residual norm, Jacobi),
+ * everything device-resident; only the scalar norm is read back once per iteration.           */
+typedef struct {
+  int32_t its;        /* iterations done                                                       */
+  int32_t reason;     /* >0 converged (2 = rtol, 3 = atol), <0 diverged (-3 = max_it)          */
+  double  rnorm;      /* last preconditioned residual norm                                     */
+  double  rnorm0;
+  double  solve_ms;   /* device time of the solve                                              */
+  uint64_t launches;
+} b200_cg_result_t;
+int b200_cg_jacobi(b200_csr_t A, const double *d_b, double *d_x, double rtol, double atol,
+                   int32_t max_it, int mode, b200_cg_result_t *res, void *stream);
+
+/* ---- synthetic workloads (device-independent, counter based) ----------------- */
+/* uniform [-1,1) from splitmix64(seed ^ i) */
+int b200_gen_vector(double *h_x, int64_t n, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SEQAIJ_H */

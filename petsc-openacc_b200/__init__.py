@@ -1,0 +1,279 @@
+"""petsc-openacc_b200 -- Blackwell-native SeqAIJ sparse mat-vec hot path.
+
+This Python module is only a ctypes view of the C ABI declared in include/b200_seqaij.h
+(libb200aij.so, hand-written CUDA for sm_100a) for tests and bench.py.  The product is the
+shared library and the PETSc-named C symbols on top of it (host/); PyTorch is used by callers for
+device memory, streams and torch.distributed only.
+
+There is no CPU fallback: importing works without a GPU (so the ABI can be inspected), but every
+compute entry point returns an error on a machine without an sm_100 device, and a missing
+library raises at import time.
+"""
+import ctypes as C
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libb200aij.so")
+
+MODE_FAST, MODE_EXACT, MODE_EXACT_FMA = 0, 1, 2
+KERNEL_AUTO, KERNEL_ROW, KERNEL_STREAM, KERNEL_VECTOR, KERNEL_MERGE, KERNEL_CPROW = range(6)
+KERNEL_NAMES = {0: "auto", 1: "row", 2: "stream", 3: "vector", 4: "merge", 5: "cprow"}
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200 error {code}: {msg}")
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile libb200aij.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-s"]
+    subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: run `make -C petsc-openacc_b200/csrc` (or "
+        "__graft_entry__.build()). There is no Python/CPU fallback for the CUDA path.")
+
+lib = C.CDLL(LIB_PATH)
+
+
+class CsrInfo(C.Structure):
+    _fields_ = [("m", C.c_int32), ("n", C.c_int32), ("nz", C.c_int32),
+                ("nonzerorowcnt", C.c_int32), ("rmax", C.c_int32),
+                ("compressedrow_use", C.c_int32), ("cprow_nrows", C.c_int32),
+                ("kernel_fast", C.c_int32), ("kernel_exact", C.c_int32),
+                ("vector_lanes", C.c_int32), ("stream_tiles", C.c_int32),
+                ("merge_tiles", C.c_int32), ("has_transpose", C.c_int32),
+                ("hist", C.c_int32 * 16), ("device_bytes", C.c_uint64)]
+
+
+class CgResult(C.Structure):
+    _fields_ = [("its", C.c_int32), ("reason", C.c_int32), ("rnorm", C.c_double),
+                ("rnorm0", C.c_double), ("solve_ms", C.c_double), ("launches", C.c_uint64)]
+
+
+lib.b200_last_error.restype = C.c_char_p
+lib.b200_version.restype = C.c_char_p
+lib.b200_launch_count.restype = C.c_uint64
+
+# every symbol include/b200_seqaij.h declares; tests check they are all exported
+ABI_SYMBOLS = [
+    "b200_init", "b200_last_error", "b200_launch_count", "b200_device_sm_count", "b200_version",
+    "b200_csr_create", "b200_csr_create_from_device", "b200_csr_update_values",
+    "b200_csr_destroy", "b200_csr_get_info", "b200_csr_set_kernel", "b200_csr_build_transpose",
+    "b200_csr_device_arrays", "b200_spmv", "b200_spmv_add", "b200_spmv_transpose",
+    "b200_spmv_transpose_add", "b200_spmv_host", "b200_spmv_add_host",
+    "b200_spmv_transpose_host", "b200_host_alloc", "b200_host_free", "b200_host_register",
+    "b200_host_unregister", "b200_vec_set", "b200_vec_copy", "b200_vec_axpy", "b200_vec_aypx",
+    "b200_vec_pointwise_mult", "b200_vec_dot", "b200_vec_norm2", "b200_vec_norm_inf",
+    "b200_vec_sum", "b200_cg_jacobi", "b200_gen_vector",
+]
+
+
+def check(rc):
+    if rc != 0:
+        raise B200Error(rc, (lib.b200_last_error() or b"").decode())
+
+
+def launch_count():
+    return int(lib.b200_launch_count())
+
+
+def init(device=0):
+    check(lib.b200_init(C.c_int(device)))
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dptr(t):
+    """device pointer of a torch CUDA tensor (float64/int32, contiguous) or a raw int"""
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(stream):
+    if stream is None:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if isinstance(stream, int):
+        return C.c_void_p(stream)
+    return C.c_void_p(stream.cuda_stream)
+
+
+class Csr:
+    """Device-resident mirror of a SeqAIJ matrix (a->i, a->j, a->a) plus its kernel plan."""
+
+    def __init__(self, ai, aj, aa, n=None):
+        ai = np.ascontiguousarray(ai, dtype=np.int32)
+        aj = np.ascontiguousarray(aj, dtype=np.int32)
+        aa = np.ascontiguousarray(aa, dtype=np.float64)
+        self.m = len(ai) - 1
+        self.n = self.m if n is None else int(n)
+        self.nz = int(ai[-1])
+        self._h = C.c_void_p(0)
+        check(lib.b200_csr_create(C.byref(self._h), C.c_int32(self.m), C.c_int32(self.n),
+                                  _np_ptr(ai), _np_ptr(aj), _np_ptr(aa)))
+
+    @classmethod
+    def from_device(cls, d_ai, d_aj, d_aa, m, n):
+        self = cls.__new__(cls)
+        self.m, self.n = int(m), int(n)
+        self._h = C.c_void_p(0)
+        check(lib.b200_csr_create_from_device(C.byref(self._h), C.c_int32(m), C.c_int32(n),
+                                              _dptr(d_ai), _dptr(d_aj), _dptr(d_aa)))
+        self.nz = self.info().nz
+        return self
+
+    def destroy(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.b200_csr_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def info(self):
+        i = CsrInfo()
+        check(lib.b200_csr_get_info(self._h, C.byref(i)))
+        return i
+
+    def set_kernel(self, kernel):
+        check(lib.b200_csr_set_kernel(self._h, C.c_int(kernel)))
+
+    def update_values(self, aa):
+        aa = np.ascontiguousarray(aa, dtype=np.float64)
+        check(lib.b200_csr_update_values(self._h, _np_ptr(aa)))
+
+    def build_transpose(self):
+        check(lib.b200_csr_build_transpose(self._h))
+
+    # device-resident vectors (torch CUDA tensors)
+    def mult(self, x, y, mode=MODE_FAST, stream=None):
+        check(lib.b200_spmv(self._h, _dptr(x), _dptr(y), C.c_int(mode), _stream(stream)))
+        return y
+
+    def mult_add(self, x, y, z, mode=MODE_FAST, stream=None):
+        check(lib.b200_spmv_add(self._h, _dptr(x), _dptr(y), _dptr(z), C.c_int(mode),
+                                _stream(stream)))
+        return z
+
+    def mult_transpose(self, x, y, mode=MODE_FAST, stream=None):
+        check(lib.b200_spmv_transpose(self._h, _dptr(x), _dptr(y), C.c_int(mode),
+                                      _stream(stream)))
+        return y
+
+    def mult_transpose_add(self, x, z, y, mode=MODE_FAST, stream=None):
+        check(lib.b200_spmv_transpose_add(self._h, _dptr(x), _dptr(z), _dptr(y), C.c_int(mode),
+                                          _stream(stream)))
+        return y
+
+    # host vectors (numpy): the MatMult_SeqAIJ(Mat,Vec,Vec) shape, synchronous
+    def mult_host(self, x, y=None, mode=MODE_FAST):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if y is None:
+            y = np.empty(self.m, dtype=np.float64)
+        check(lib.b200_spmv_host(self._h, _np_ptr(x), _np_ptr(y), C.c_int(mode)))
+        return y
+
+    def mult_add_host(self, x, y, z=None, mode=MODE_FAST):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if z is None:
+            z = np.empty(self.m, dtype=np.float64)
+        check(lib.b200_spmv_add_host(self._h, _np_ptr(x), _np_ptr(y), _np_ptr(z), C.c_int(mode)))
+        return z
+
+    def mult_transpose_host(self, x, y=None, mode=MODE_FAST):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if y is None:
+            y = np.empty(self.n, dtype=np.float64)
+        check(lib.b200_spmv_transpose_host(self._h, _np_ptr(x), _np_ptr(y), C.c_int(mode)))
+        return y
+
+    def cg_jacobi(self, b, x, rtol=1e-14, atol=1e-12, max_it=10000, mode=MODE_FAST, stream=None):
+        res = CgResult()
+        check(lib.b200_cg_jacobi(self._h, _dptr(b), _dptr(x), C.c_double(rtol), C.c_double(atol),
+                                 C.c_int32(max_it), C.c_int(mode), C.byref(res), _stream(stream)))
+        return res
+
+
+def gen_vector(n, seed=0xB200):
+    x = np.empty(n, dtype=np.float64)
+    check(lib.b200_gen_vector(_np_ptr(x), C.c_int64(n), C.c_uint64(seed)))
+    return x
+
+
+class PinnedArray:
+    """float64 numpy view of page-locked host memory from b200_host_alloc."""
+
+    def __init__(self, n):
+        self._p = C.c_void_p(0)
+        self.n = int(n)
+        check(lib.b200_host_alloc(C.byref(self._p), C.c_size_t(max(self.n, 1) * 8)))
+        buf = (C.c_double * self.n).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=self.n)
+
+    def free(self):
+        if self._p.value:
+            self.array = None
+            lib.b200_host_free(self._p)
+            self._p = C.c_void_p(0)
+
+
+# vector ops on torch CUDA tensors; reductions write into a 1-element CUDA tensor
+def vec_dot(x, y, out, stream=None):
+    check(lib.b200_vec_dot(_dptr(x), _dptr(y), C.c_int64(x.numel()), _dptr(out), _stream(stream)))
+
+
+def vec_norm2(x, out, stream=None):
+    check(lib.b200_vec_norm2(_dptr(x), C.c_int64(x.numel()), _dptr(out), _stream(stream)))
+
+
+def vec_norm_inf(x, out, stream=None):
+    check(lib.b200_vec_norm_inf(_dptr(x), C.c_int64(x.numel()), _dptr(out), _stream(stream)))
+
+
+def vec_sum(x, out, stream=None):
+    check(lib.b200_vec_sum(_dptr(x), C.c_int64(x.numel()), _dptr(out), _stream(stream)))
+
+
+def vec_axpy(y, a, x, stream=None):
+    check(lib.b200_vec_axpy(_dptr(y), C.c_double(a), _dptr(x), C.c_int64(x.numel()),
+                            _stream(stream)))
+
+
+def vec_aypx(y, a, x, stream=None):
+    check(lib.b200_vec_aypx(_dptr(y), C.c_double(a), _dptr(x), C.c_int64(x.numel()),
+                            _stream(stream)))
+
+
+def vec_set(x, a, stream=None):
+    check(lib.b200_vec_set(_dptr(x), C.c_double(a), C.c_int64(x.numel()), _stream(stream)))
+
+
+def vec_copy(y, x, stream=None):
+    check(lib.b200_vec_copy(_dptr(y), _dptr(x), C.c_int64(x.numel()), _stream(stream)))
+
+
+def vec_pointwise_mult(w, x, y, stream=None):
+    check(lib.b200_vec_pointwise_mult(_dptr(w), _dptr(x), _dptr(y), C.c_int64(x.numel()),
+                                      _stream(stream)))

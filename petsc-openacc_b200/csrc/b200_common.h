@@ -1,0 +1,124 @@
+// b200_common.h -- error plumbing, launch accounting and PTX helpers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/b200_seqaij.h"
+
+namespace b200 {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t>    g_launches;
+
+int  set_error(int code, const char *fmt, ...);
+int  ensure_device();        // B200_OK when an sm_100 device is current
+int  sm_count();
+int  env_int(const char *name, int dflt);
+
+#define B200_CUDA_TRY(expr)                                                                    \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return b200::set_error(B200_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,       \
+                             cudaGetErrorString(_e));                                          \
+  } while (0)
+
+#define B200_TRY(expr)                                                                         \
+  do {                                                                                         \
+    int _r = (expr);                                                                           \
+    if (_r) return _r;                                                                         \
+  } while (0)
+
+// every kernel launch of the library goes through this so b200_launch_count() is honest
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                                    \
+  do {                                                                                         \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                \
+    b200::g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+    B200_CUDA_TRY(cudaGetLastError());                                                         \
+  } while (0)
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk-copy (TMA engine, 1-D) helpers.  SASS: SYNCS.* and UBLKCP.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t addr = smem_u32(bar), done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar, uint64_t policy)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+// streaming (read-once) vector loads that do not allocate in L1
+__device__ __forceinline__ double2 ldg_stream_f64x2(const double *p)
+{
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+               : "=d"(v.x), "=d"(v.y)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int4 ldg_stream_s32x4(const int *p)
+{
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+#endif  // __CUDACC__
+
+}  // namespace b200

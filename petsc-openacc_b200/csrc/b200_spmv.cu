@@ -1,0 +1,876 @@
+// b200_spmv.cu -- SeqAIJ sparse mat-vec kernel family for sm_100a and the C ABI around it.
+//
+// What it replaces: the single OpenACC compute region of the reference,
+//   src/openacc-step1/MatMult_SeqAIJ.patch:19-32  (K1)  ... step4 :55-88 (K4a/K4b),
+// i.e. PETSc 3.7.6 MatMult_SeqAIJ's row loop, plus MatMultAdd / MatMultTranspose[Add] which the
+// reference leaves on the CPU.  Not a port: the matrix streams through shared memory with the
+// TMA engine's bulk copies (cp.async.bulk + mbarrier ring) in a persistent, warp-specialised
+// kernel, each row is then summed by one thread strictly left to right out of shared memory,
+// which makes the fast path of short-row matrices bit-reproducible against the CPU loop.
+//
+// Kernels (all fp64 values, int32 indices):
+//   k_row     thread per row from global memory          -- the reference's launch shape
+//   k_stream  bulk-copy staged CSR tiles, thread per row -- default for short, regular rows
+//   k_vector  LANES lanes per row + __shfl_xor reduction -- medium rows
+//   k_cprow   compressed-row (only non-empty rows)       -- off-diagonal block B of MPIAIJ
+//   k_tr_atomic  A^T x by fp64 atomics                   -- transpose without a second copy
+#include <algorithm>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "b200_common.h"
+
+namespace b200 {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t>    g_launches{0};
+
+int set_error(int code, const char *fmt, ...)
+{
+  char    buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int env_int(const char *name, int dflt)
+{
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+static int g_sm_count = 0;
+static int g_dev_ok   = -1;
+
+int ensure_device()
+{
+  if (g_dev_ok == 1) return B200_OK;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_error(B200_ERR_NO_DEVICE, "no CUDA device visible: the b200 library has no CPU fallback");
+  }
+  int dev = 0;
+  B200_CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  B200_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+  if (p.major != 10)
+    return set_error(B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                     dev, p.major, p.minor);
+  g_sm_count = p.multiProcessorCount;
+  g_dev_ok   = 1;
+  return B200_OK;
+}
+int sm_count() { return g_sm_count; }
+
+}  // namespace b200
+
+using namespace b200;
+
+// =============================================================================================
+// device code
+// =============================================================================================
+template <int MODE>
+__device__ __forceinline__ double acc(double s, double a, double x)
+{
+  // EXACT: product and sum rounded separately, like the oracle built with -ffp-contract=off.
+  if (MODE == B200_MODE_EXACT) return __dadd_rn(s, __dmul_rn(a, x));
+  return __fma_rn(a, x, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_row: one thread per row, left to right, straight from global memory.
+// Same launch shape as the reference's `gang vector(32)` loop
+// (src/openacc-step1/MatMult_SeqAIJ.patch:19-32); kept as the simplest deterministic kernel.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, bool ADD>
+__global__ void __launch_bounds__(128) k_row(int m, const int *__restrict__ ii,
+                                             const int *__restrict__ aj,
+                                             const double *__restrict__ aa,
+                                             const double *__restrict__ x, const double *yin,
+                                             double *y)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  int    lo = ii[i], hi = ii[i + 1];
+  double sum = ADD ? yin[i] : 0.0;
+  for (int k = lo; k < hi; ++k) sum = acc<MODE>(sum, aa[k], __ldg(x + aj[k]));
+  y[i] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_vector: LANES lanes per row, strided partial sums, butterfly reduction.
+// ---------------------------------------------------------------------------------------------
+template <int LANES, bool ADD>
+__global__ void __launch_bounds__(256) k_vector(int m, const int *__restrict__ ii,
+                                                const int *__restrict__ aj,
+                                                const double *__restrict__ aa,
+                                                const double *__restrict__ x, const double *yin,
+                                                double *y)
+{
+  long long t    = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int       row  = (int)(t / LANES);
+  int       lane = (int)(t % LANES);
+  double    sum  = 0.0;
+  int       lo = 0, hi = 0;
+  if (row < m) { lo = __ldg(ii + row); hi = __ldg(ii + row + 1); }
+  for (int k = lo + lane; k < hi; k += LANES) sum = __fma_rn(aa[k], __ldg(x + aj[k]), sum);
+#pragma unroll
+  for (int off = LANES / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off, LANES);
+  if (row < m && lane == 0) y[row] = ADD ? yin[row] + sum : sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_stream: persistent, warp-specialised.  One producer lane drives the TMA engine: for each tile
+// it bulk-copies the tile's slice of aa, aj and ii into a ring of shared-memory stages
+// (cp.async.bulk ... mbarrier::complete_tx, evict-first in L2: the matrix is read exactly once).
+// THREADS consumer threads own one row each and sum it left to right out of shared memory;
+// x is gathered through the read-only path (L1/L2 resident window for banded matrices, and for
+// stencil matrices lane = consecutive rows makes every gather a contiguous 256-byte request).
+// tiles[t] = {first row, last row + 1, ii[first], ii[last + 1]}.
+// ---------------------------------------------------------------------------------------------
+#define STREAM_PAD 16  // alignment slack (<= 3 + 3) + predicated read-ahead (<= 7)
+#define STREAM_U 8
+
+__host__ __device__ inline size_t stream_stage_bytes(int threads, int cap)
+{
+  return (size_t)(cap + STREAM_PAD) * 12 + (size_t)(threads + 8) * 4;
+}
+
+template <int MODE, bool ADD, int THREADS>
+__global__ void __launch_bounds__(THREADS + 32)
+    k_stream(const int4 *__restrict__ tiles, int ntiles, const int *__restrict__ ii,
+             const int *__restrict__ aj, const double *__restrict__ aa,
+             const double *__restrict__ x, const double *yin, double *y, int cap, int stages)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full  = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty = full + stages;
+  unsigned char *stage0 = smem + 128;  // barriers live in the first 128 bytes (stages <= 8)
+  const size_t   sbytes = stream_stage_bytes(THREADS, cap);
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (tid >= THREADS) {
+    // ------------------------------- producer warp -------------------------------------------
+    if (tid == THREADS) {
+      const uint64_t pol = l2_policy_evict_first();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % stages;
+        if (it >= stages) mbar_wait(&empty[s], ((it / stages) - 1) & 1);
+        const int4 d   = __ldg(tiles + tile);
+        const int  s4  = d.z & ~3;
+        const int  nn  = ((d.w + 3) & ~3) - s4;
+        const int  r0a = d.x & ~3;
+        const int  nr  = ((d.y + 1 + 3) & ~3) - r0a;
+        unsigned char *st  = stage0 + (size_t)s * sbytes;
+        double        *saa = reinterpret_cast<double *>(st);
+        int           *saj = reinterpret_cast<int *>(st + (size_t)(cap + STREAM_PAD) * 8);
+        int           *sii = saj + (cap + STREAM_PAD);
+        mbar_expect_tx(&full[s], (uint32_t)(nn * 12 + nr * 4));
+        if (nn > 0) {
+          bulk_g2s(saa, aa + s4, (uint32_t)nn * 8, &full[s], pol);
+          bulk_g2s(saj, aj + s4, (uint32_t)nn * 4, &full[s], pol);
+        }
+        bulk_g2s(sii, ii + r0a, (uint32_t)nr * 4, &full[s], pol);
+      }
+    }
+    return;
+  }
+
+  // --------------------------------- consumers -------------------------------------------------
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int  s = it % stages;
+    const int4 d = __ldg(tiles + tile);
+    unsigned char *st  = stage0 + (size_t)s * sbytes;
+    const double  *saa = reinterpret_cast<const double *>(st);
+    const int     *saj = reinterpret_cast<const int *>(st + (size_t)(cap + STREAM_PAD) * 8);
+    const int     *sii = saj + (cap + STREAM_PAD) + (d.x & 3);
+    const int      r   = d.x + tid;
+    double sum = 0.0;
+    if (ADD) { if (r < d.y) sum = yin[r]; }
+    mbar_wait(&full[s], (it / stages) & 1);
+    if (r < d.y) {
+      const int lo = sii[tid], hi = sii[tid + 1];
+      const int p  = lo - (d.z & ~3);
+      const int n  = hi - lo;
+      for (int k = 0; k < n; k += STREAM_U) {
+        double av[STREAM_U], xv[STREAM_U];
+#pragma unroll
+        for (int j = 0; j < STREAM_U; ++j) {
+          const bool ok = (k + j) < n;
+          av[j] = saa[p + k + j];
+          int c = saj[p + k + j];
+          xv[j] = ok ? __ldg(x + c) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < STREAM_U; ++j)
+          if ((k + j) < n) sum = acc<MODE>(sum, av[j], xv[j]);
+      }
+      y[r] = sum;
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_cprow: compressed-row MatMultAdd / MatMult [P376 MatMult_SeqAIJ compressed branch]: only the
+// cprow.nrows non-empty rows are touched (the off-diagonal block B has ~2% non-empty rows).
+// For MatMult (ADD = false) y has been zeroed by the caller.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, bool ADD>
+__global__ void __launch_bounds__(128) k_cprow(int nrows, const int *__restrict__ cpi,
+                                               const int *__restrict__ ridx,
+                                               const int *__restrict__ aj,
+                                               const double *__restrict__ aa,
+                                               const double *__restrict__ x, const double *yin,
+                                               double *y)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows) return;
+  int    lo = cpi[t], hi = cpi[t + 1], i = ridx[t];
+  double sum = ADD ? yin[i] : 0.0;
+  for (int k = lo; k < hi; ++k) sum = acc<MODE>(sum, aa[k], __ldg(x + aj[k]));
+  y[i] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tr_atomic: y[aj[k]] += x[i]*aa[k] with fp64 atomics (RED.E.ADD.F64); y pre-initialised.
+// Run-to-run order is not fixed, so this serves MODE_FAST only.
+// ---------------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(256) k_tr_atomic(int m, const int *__restrict__ ii,
+                                                   const int *__restrict__ aj,
+                                                   const double *__restrict__ aa,
+                                                   const double *__restrict__ x, double *y)
+{
+  long long t    = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int       row  = (int)(t / LANES);
+  int       lane = (int)(t % LANES);
+  if (row >= m) return;
+  const double alpha = x[row];
+  const int    lo = ii[row], hi = ii[row + 1];
+  for (int k = lo + lane; k < hi; k += LANES) atomicAdd(y + aj[k], alpha * aa[k]);
+}
+
+__global__ void k_copy(double *__restrict__ dst, const double *__restrict__ src, long long n)
+{
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long s = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += s) dst[i] = src[i];
+}
+
+// =============================================================================================
+// host side: the handle, the plan, the C ABI
+// =============================================================================================
+struct b200_csr_s {
+  int32_t m = 0, n = 0, nz = 0;
+  int    *d_ai = nullptr, *d_aj = nullptr;
+  double *d_aa = nullptr;
+  // statistics (MatAssemblyEnd_SeqAIJ bookkeeping)
+  int32_t nonzerorowcnt = 0, rmax = 0;
+  int32_t hist[16]      = {0};
+  // compressed row (MatCheckCompressedRow, ratio 0.6)
+  bool    cprow_use = false;
+  int32_t cprow_nrows = 0;
+  int    *d_cpi = nullptr, *d_ridx = nullptr;
+  // stream plan
+  int4   *d_tiles = nullptr;
+  int32_t ntiles = 0, stream_threads = 256, stream_cap = 0, stream_stages = 0, stream_grid = 0;
+  size_t  stream_smem = 0;
+  // vector plan
+  int32_t vector_lanes = 8;
+  int32_t kernel_fast = B200_KERNEL_ROW, kernel_exact = B200_KERNEL_ROW, kernel_override = 0;
+  // explicit transpose (n x m), built lazily
+  b200_csr_s *T = nullptr;
+  // host-vector path scratch
+  double      *d_hx = nullptr, *d_hy = nullptr;
+  size_t       hx_len = 0, hy_len = 0;
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t  hev[2] = {nullptr, nullptr};
+  uint64_t     device_bytes = 0;
+};
+
+static int hist_bucket(int len)
+{
+  if (len <= 2) return len;  // 0,1,2
+  int b = 3, hi = 4;         // [3-4],[5-8],[9-16],...
+  while (len > hi && b < 15) { hi <<= 1; ++b; }
+  return b;
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t count, b200_csr_s *A)
+{
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  B200_CUDA_TRY(cudaMalloc((void **)p, bytes));
+  if (A) A->device_bytes += bytes;
+  return B200_OK;
+}
+
+template <int THREADS>
+static int stream_occupancy(size_t smem, int *ctas)
+{
+  auto kern = k_stream<B200_MODE_EXACT_FMA, false, THREADS>;  // any instantiation: same footprint
+  B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, kern, THREADS + 32, smem));
+  return B200_OK;
+}
+
+template <int MODE, bool ADD, int THREADS>
+static int stream_set_attr(size_t smem)
+{
+  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, ADD, THREADS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return B200_OK;
+}
+
+static int stream_set_all_attrs(int threads, size_t smem)
+{
+  if (threads == 256) {
+    B200_TRY((stream_set_attr<B200_MODE_EXACT, false, 256>(smem)));
+    B200_TRY((stream_set_attr<B200_MODE_EXACT, true, 256>(smem)));
+    B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, false, 256>(smem)));
+    B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, true, 256>(smem)));
+  } else {
+    B200_TRY((stream_set_attr<B200_MODE_EXACT, false, 128>(smem)));
+    B200_TRY((stream_set_attr<B200_MODE_EXACT, true, 128>(smem)));
+    B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, false, 128>(smem)));
+    B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, true, 128>(smem)));
+  }
+  return B200_OK;
+}
+
+// Build the plan from the host row-pointer array.
+static int build_plan(b200_csr_s *A, const int32_t *ai)
+{
+  const int m = A->m;
+  // --- statistics ---------------------------------------------------------------------------
+  A->nonzerorowcnt = 0;
+  A->rmax          = 0;
+  memset(A->hist, 0, sizeof A->hist);
+  for (int i = 0; i < m; ++i) {
+    int len = ai[i + 1] - ai[i];
+    A->nonzerorowcnt += (len > 0);
+    A->rmax = std::max(A->rmax, len);
+    A->hist[hist_bucket(len)]++;
+  }
+  // --- compressed row: zero rows >= 0.6 m ([P376] MatCheckCompressedRow, ratio at
+  //     src/openacc-step2/MatAssemblyEnd_SeqAIJ.patch:35 context) -----------------------------
+  const int nzero = m - A->nonzerorowcnt;
+  A->cprow_use    = !(nzero < 0.6 * m) && m > 0;
+  if (A->cprow_use) {
+    std::vector<int> cpi(A->nonzerorowcnt + 1), ridx(std::max(A->nonzerorowcnt, 1));
+    int row = 0;
+    cpi[0]  = 0;
+    for (int i = 0; i < m; ++i) {
+      if (ai[i + 1] == ai[i]) continue;
+      cpi[row + 1] = ai[i + 1];
+      ridx[row++]  = i;
+    }
+    A->cprow_nrows = row;
+    B200_TRY(dev_alloc(&A->d_cpi, cpi.size(), A));
+    B200_TRY(dev_alloc(&A->d_ridx, ridx.size(), A));
+    B200_CUDA_TRY(cudaMemcpy(A->d_cpi, cpi.data(), cpi.size() * sizeof(int), cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpy(A->d_ridx, ridx.data(), ridx.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  // --- stream tiles ---------------------------------------------------------------------------
+  const double mean = A->nonzerorowcnt ? (double)A->nz / A->nonzerorowcnt : 0.0;
+  int threads = env_int("B200_STREAM_THREADS", mean <= 12.0 ? 256 : 128);
+  if (threads != 128 && threads != 256) threads = 256;
+  int cap = env_int("B200_STREAM_CAP", 0);
+  if (cap <= 0) {
+    cap = (int)(threads * std::max(mean, 1.0) * 1.125) + 64;
+    cap = std::min(cap, 8192);
+  }
+  cap = std::max((cap + 3) & ~3, 64);
+  int stages = env_int("B200_STREAM_STAGES", 0);
+  A->ntiles  = 0;
+  bool stream_ok = (m > 0 && A->nz > 0 && A->rmax <= cap);
+  if (stream_ok) {
+    std::vector<int4> tiles;
+    tiles.reserve((size_t)m / threads + (size_t)A->nz / cap + 2);
+    int r = 0;
+    while (r < m) {
+      int r1 = std::min(m, r + threads);
+      if (ai[r1] - ai[r] > cap) {
+        const int32_t *ub = std::upper_bound(ai + r, ai + r1 + 1, ai[r] + cap);
+        r1 = (int)(ub - ai) - 1;
+      }
+      if (r1 <= r) { stream_ok = false; break; }
+      tiles.push_back(make_int4(r, r1, ai[r], ai[r1]));
+      r = r1;
+    }
+    if (stream_ok) {
+      const size_t sbytes = stream_stage_bytes(threads, cap);
+      if (stages <= 0) {
+        // two CTAs per SM, as many stages as fit under ~110 KB per CTA
+        stages = (int)std::min<size_t>(8, std::max<size_t>(2, (110 * 1024 - 128) / sbytes));
+      }
+      stages = std::min(std::max(stages, 2), 8);
+      A->stream_smem = 128 + (size_t)stages * sbytes;
+      if (A->stream_smem > 227 * 1024) { stages = 2; A->stream_smem = 128 + 2 * sbytes; }
+      if (A->stream_smem > 227 * 1024) stream_ok = false;
+    }
+    if (stream_ok) {
+      A->ntiles = (int)tiles.size();
+      A->stream_threads = threads;
+      A->stream_cap     = cap;
+      A->stream_stages  = stages;
+      B200_TRY(dev_alloc(&A->d_tiles, tiles.size(), A));
+      B200_CUDA_TRY(cudaMemcpy(A->d_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+      B200_TRY(stream_set_all_attrs(threads, A->stream_smem));
+      int ctas = 0;
+      if (threads == 256) B200_TRY(stream_occupancy<256>(A->stream_smem, &ctas));
+      else B200_TRY(stream_occupancy<128>(A->stream_smem, &ctas));
+      if (ctas < 1) stream_ok = false;
+      int want = env_int("B200_STREAM_CTAS_PER_SM", ctas);
+      ctas     = std::max(1, std::min(ctas, want));
+      A->stream_grid = std::min(A->ntiles, sm_count() * ctas);
+    }
+  }
+  if (!stream_ok) A->ntiles = 0;
+  // --- vector lanes: smallest power of two >= mean row length, 2..32 ---------------------------
+  int lanes = 2;
+  while (lanes < 32 && lanes < mean) lanes <<= 1;
+  A->vector_lanes = lanes;
+  // --- choice -----------------------------------------------------------------------------------
+  // EXACT needs one accumulator per row: stream when every row fits a stage, else thread per row.
+  A->kernel_exact = A->cprow_use ? B200_KERNEL_CPROW : (A->ntiles ? B200_KERNEL_STREAM : B200_KERNEL_ROW);
+  // FAST: rows of similar, short length -> stream (SIMT lanes stay balanced);
+  //       otherwise sub-warp vector kernel.
+  const bool regular = A->rmax <= std::max(32.0, 4.0 * mean);
+  if (A->cprow_use) A->kernel_fast = B200_KERNEL_CPROW;
+  else if (A->ntiles && regular) A->kernel_fast = B200_KERNEL_STREAM;
+  else if (mean >= 2.0) A->kernel_fast = B200_KERNEL_VECTOR;
+  else A->kernel_fast = B200_KERNEL_ROW;
+  return B200_OK;
+}
+
+static int create_common(b200_csr_s *A, const int32_t *h_ai)
+{
+  return build_plan(A, h_ai);
+}
+
+extern "C" int b200_init(int device)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_error(B200_ERR_NO_DEVICE, "no CUDA device visible: the b200 library has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return set_error(B200_ERR_ARG, "device %d out of range [0,%d)", device, n);
+  B200_CUDA_TRY(cudaSetDevice(device));
+  g_dev_ok = -1;
+  return ensure_device();
+}
+
+extern "C" const char *b200_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint64_t    b200_launch_count(void) { return g_launches.load(); }
+extern "C" int         b200_device_sm_count(void) { return ensure_device() ? 0 : sm_count(); }
+extern "C" const char *b200_version(void) { return "b200-seqaij 0.1 (sm_100a)"; }
+
+static int alloc_mirrors(b200_csr_s *A)
+{
+  // +8 elements of slack: the bulk copies round tile ends up to 16-byte multiples
+  B200_TRY(dev_alloc(&A->d_ai, (size_t)A->m + 1 + 8, A));
+  B200_TRY(dev_alloc(&A->d_aj, (size_t)A->nz + 8, A));
+  B200_TRY(dev_alloc(&A->d_aa, (size_t)A->nz + 8, A));
+  B200_CUDA_TRY(cudaMemset(A->d_aj + A->nz, 0, 8 * sizeof(int)));
+  B200_CUDA_TRY(cudaMemset(A->d_aa + A->nz, 0, 8 * sizeof(double)));
+  return B200_OK;
+}
+
+static int fill_ai_tail(b200_csr_s *A)
+{
+  int tail[8];
+  for (int k = 0; k < 8; ++k) tail[k] = A->nz;
+  B200_CUDA_TRY(cudaMemcpy(A->d_ai + A->m + 1, tail, sizeof tail, cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
+extern "C" int b200_csr_create(b200_csr_t *out, int32_t m, int32_t n, const int32_t *h_ai,
+                               const int32_t *h_aj, const double *h_aa)
+{
+  if (!out || m < 0 || n < 0 || !h_ai) return set_error(B200_ERR_ARG, "b200_csr_create: bad argument");
+  B200_TRY(ensure_device());
+  const int32_t nz = h_ai[m];
+  if (nz < 0 || h_ai[0] != 0) return set_error(B200_ERR_ARG, "b200_csr_create: ai[0] must be 0 and ai[m] >= 0");
+  if (nz > 0 && (!h_aj || !h_aa)) return set_error(B200_ERR_ARG, "b200_csr_create: null aj/aa with nz > 0");
+  b200_csr_s *A = new (std::nothrow) b200_csr_s;
+  if (!A) return set_error(B200_ERR_MEM, "out of host memory");
+  A->m = m; A->n = n; A->nz = nz;
+  int rc = alloc_mirrors(A);
+  if (!rc) rc = [&]() -> int {
+    B200_CUDA_TRY(cudaMemcpy(A->d_ai, h_ai, ((size_t)m + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    B200_TRY(fill_ai_tail(A));
+    if (nz) {
+      B200_CUDA_TRY(cudaMemcpy(A->d_aj, h_aj, (size_t)nz * sizeof(int), cudaMemcpyHostToDevice));
+      B200_CUDA_TRY(cudaMemcpy(A->d_aa, h_aa, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return create_common(A, h_ai);
+  }();
+  if (rc) { b200_csr_destroy(A); return rc; }
+  *out = A;
+  return B200_OK;
+}
+
+extern "C" int b200_csr_create_from_device(b200_csr_t *out, int32_t m, int32_t n,
+                                           const int32_t *d_ai, const int32_t *d_aj,
+                                           const double *d_aa)
+{
+  if (!out || m < 0 || n < 0 || !d_ai) return set_error(B200_ERR_ARG, "b200_csr_create_from_device: bad argument");
+  B200_TRY(ensure_device());
+  std::vector<int32_t> h_ai((size_t)m + 1);
+  B200_CUDA_TRY(cudaMemcpy(h_ai.data(), d_ai, h_ai.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  const int32_t nz = h_ai[m];
+  b200_csr_s *A = new (std::nothrow) b200_csr_s;
+  if (!A) return set_error(B200_ERR_MEM, "out of host memory");
+  A->m = m; A->n = n; A->nz = nz;
+  int rc = alloc_mirrors(A);
+  if (!rc) rc = [&]() -> int {
+    B200_CUDA_TRY(cudaMemcpy(A->d_ai, d_ai, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToDevice));
+    B200_TRY(fill_ai_tail(A));
+    if (nz) {
+      B200_CUDA_TRY(cudaMemcpy(A->d_aj, d_aj, (size_t)nz * sizeof(int), cudaMemcpyDeviceToDevice));
+      B200_CUDA_TRY(cudaMemcpy(A->d_aa, d_aa, (size_t)nz * sizeof(double), cudaMemcpyDeviceToDevice));
+    }
+    return create_common(A, h_ai.data());
+  }();
+  if (rc) { b200_csr_destroy(A); return rc; }
+  *out = A;
+  return B200_OK;
+}
+
+extern "C" int b200_csr_update_values(b200_csr_t A, const double *h_aa)
+{
+  if (!A || (!h_aa && A->nz)) return set_error(B200_ERR_ARG, "b200_csr_update_values: bad argument");
+  if (A->nz) B200_CUDA_TRY(cudaMemcpy(A->d_aa, h_aa, (size_t)A->nz * sizeof(double), cudaMemcpyHostToDevice));
+  if (A->T) { b200_csr_destroy(A->T); A->T = nullptr; }  // stale transpose values
+  return B200_OK;
+}
+
+extern "C" int b200_csr_destroy(b200_csr_t A)
+{
+  if (!A) return B200_OK;
+  if (A->T) b200_csr_destroy(A->T);
+  cudaFree(A->d_ai); cudaFree(A->d_aj); cudaFree(A->d_aa);
+  cudaFree(A->d_cpi); cudaFree(A->d_ridx); cudaFree(A->d_tiles);
+  cudaFree(A->d_hx); cudaFree(A->d_hy);
+  for (auto &s : A->hs) if (s) cudaStreamDestroy(s);
+  for (auto &e : A->hev) if (e) cudaEventDestroy(e);
+  delete A;
+  return B200_OK;
+}
+
+extern "C" int b200_csr_get_info(b200_csr_t A, b200_csr_info_t *info)
+{
+  if (!A || !info) return set_error(B200_ERR_ARG, "b200_csr_get_info: bad argument");
+  memset(info, 0, sizeof *info);
+  info->m = A->m; info->n = A->n; info->nz = A->nz;
+  info->nonzerorowcnt = A->nonzerorowcnt; info->rmax = A->rmax;
+  info->compressedrow_use = A->cprow_use; info->cprow_nrows = A->cprow_nrows;
+  info->kernel_fast = A->kernel_fast; info->kernel_exact = A->kernel_exact;
+  info->vector_lanes = A->vector_lanes; info->stream_tiles = A->ntiles;
+  info->merge_tiles = 0; info->has_transpose = A->T != nullptr;
+  memcpy(info->hist, A->hist, sizeof A->hist);
+  info->device_bytes = A->device_bytes + (A->T ? A->T->device_bytes : 0);
+  return B200_OK;
+}
+
+extern "C" int b200_csr_set_kernel(b200_csr_t A, int kernel)
+{
+  if (!A || kernel < 0 || kernel > B200_KERNEL_CPROW) return set_error(B200_ERR_ARG, "b200_csr_set_kernel: bad argument");
+  if (kernel == B200_KERNEL_STREAM && !A->ntiles) return set_error(B200_ERR_STATE, "stream kernel not applicable: a row exceeds the stage capacity");
+  if (kernel == B200_KERNEL_CPROW && !A->cprow_use) return set_error(B200_ERR_STATE, "matrix has no compressed-row index");
+  if (kernel == B200_KERNEL_MERGE) return set_error(B200_ERR_STATE, "merge kernel not built for this matrix");
+  A->kernel_override = kernel;
+  return B200_OK;
+}
+
+extern "C" int b200_csr_device_arrays(b200_csr_t A, const int32_t **d_ai, const int32_t **d_aj,
+                                      const double **d_aa)
+{
+  if (!A) return set_error(B200_ERR_ARG, "null handle");
+  if (d_ai) *d_ai = A->d_ai;
+  if (d_aj) *d_aj = A->d_aj;
+  if (d_aa) *d_aa = A->d_aa;
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------
+template <int MODE, bool ADD>
+static int launch_stream(b200_csr_s *A, const double *x, const double *yin, double *y, cudaStream_t st)
+{
+  if (A->stream_threads == 256)
+    B200_LAUNCH((k_stream<MODE, ADD, 256>), A->stream_grid, 256 + 32, A->stream_smem, st, A->d_tiles,
+                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages);
+  else
+    B200_LAUNCH((k_stream<MODE, ADD, 128>), A->stream_grid, 128 + 32, A->stream_smem, st, A->d_tiles,
+                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages);
+  return B200_OK;
+}
+
+template <bool ADD>
+static int launch_vector(b200_csr_s *A, const double *x, const double *yin, double *y, cudaStream_t st)
+{
+  const int       L      = A->vector_lanes;
+  const long long thr    = (long long)A->m * L;
+  const unsigned  blocks = (unsigned)((thr + 255) / 256);
+  switch (L) {
+    case 2: B200_LAUNCH((k_vector<2, ADD>), blocks, 256, 0, st, A->m, A->d_ai, A->d_aj, A->d_aa, x, yin, y); break;
+    case 4: B200_LAUNCH((k_vector<4, ADD>), blocks, 256, 0, st, A->m, A->d_ai, A->d_aj, A->d_aa, x, yin, y); break;
+    case 8: B200_LAUNCH((k_vector<8, ADD>), blocks, 256, 0, st, A->m, A->d_ai, A->d_aj, A->d_aa, x, yin, y); break;
+    case 16: B200_LAUNCH((k_vector<16, ADD>), blocks, 256, 0, st, A->m, A->d_ai, A->d_aj, A->d_aa, x, yin, y); break;
+    default: B200_LAUNCH((k_vector<32, ADD>), blocks, 256, 0, st, A->m, A->d_ai, A->d_aj, A->d_aa, x, yin, y); break;
+  }
+  return B200_OK;
+}
+
+template <int MODE, bool ADD>
+static int launch_mode(b200_csr_s *A, int kernel, const double *x, const double *yin, double *y, cudaStream_t st)
+{
+  switch (kernel) {
+    case B200_KERNEL_STREAM: return launch_stream<MODE, ADD>(A, x, yin, y, st);
+    case B200_KERNEL_CPROW:
+      if (!ADD) B200_CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)A->m * sizeof(double), st));
+      else if (yin != y) {
+        B200_LAUNCH(k_copy, std::max(1, std::min(sm_count() * 8, (A->m + 255) / 256)), 256, 0, st, y, yin, (long long)A->m);
+        yin = y;
+      }
+      if (A->cprow_nrows)
+        B200_LAUNCH((k_cprow<MODE, ADD>), (A->cprow_nrows + 127) / 128, 128, 0, st, A->cprow_nrows,
+                    A->d_cpi, A->d_ridx, A->d_aj, A->d_aa, x, yin, y);
+      return B200_OK;
+    case B200_KERNEL_ROW:
+    default:
+      B200_LAUNCH((k_row<MODE, ADD>), (A->m + 127) / 128, 128, 0, st, A->m, A->d_ai, A->d_aj, A->d_aa, x, yin, y);
+      return B200_OK;
+  }
+}
+
+template <bool ADD>
+static int spmv_dispatch(b200_csr_s *A, const double *x, const double *yin, double *y, int mode, cudaStream_t st)
+{
+  if (A->m == 0) return B200_OK;
+  int kernel = A->kernel_override;
+  if (!kernel) kernel = (mode == B200_MODE_FAST) ? A->kernel_fast : A->kernel_exact;
+  if (mode != B200_MODE_FAST && (kernel == B200_KERNEL_VECTOR || kernel == B200_KERNEL_MERGE))
+    return set_error(B200_ERR_ARG, "kernel %d cannot honour an EXACT summation order", kernel);
+  if (kernel == B200_KERNEL_VECTOR) return launch_vector<ADD>(A, x, yin, y, st);
+  if (mode == B200_MODE_EXACT) return launch_mode<B200_MODE_EXACT, ADD>(A, kernel, x, yin, y, st);
+  return launch_mode<B200_MODE_EXACT_FMA, ADD>(A, kernel, x, yin, y, st);
+}
+
+static int check_mode(int mode)
+{
+  if (mode < B200_MODE_FAST || mode > B200_MODE_EXACT_FMA) return set_error(B200_ERR_ARG, "unknown mode %d", mode);
+  return B200_OK;
+}
+
+extern "C" int b200_spmv(b200_csr_t A, const double *d_x, double *d_y, int mode, void *stream)
+{
+  if (!A || (!d_x && A->n) || (!d_y && A->m)) return set_error(B200_ERR_ARG, "b200_spmv: null argument");
+  if (d_x == d_y && A->m) return set_error(B200_ERR_ARG, "b200_spmv: x and y must differ (MatMult contract)");
+  B200_TRY(check_mode(mode));
+  return spmv_dispatch<false>(A, d_x, nullptr, d_y, mode, (cudaStream_t)stream);
+}
+
+extern "C" int b200_spmv_add(b200_csr_t A, const double *d_x, const double *d_y, double *d_z,
+                             int mode, void *stream)
+{
+  if (!A || (!d_x && A->n) || ((!d_y || !d_z) && A->m)) return set_error(B200_ERR_ARG, "b200_spmv_add: null argument");
+  if ((d_x == d_z) && A->m) return set_error(B200_ERR_ARG, "b200_spmv_add: x and z must differ");
+  B200_TRY(check_mode(mode));
+  return spmv_dispatch<true>(A, d_x, d_y, d_z, mode, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// transpose: explicit copy (deterministic, ascending-row order per column = the reference's
+// scatter order) or atomics.
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200_csr_build_transpose(b200_csr_t A)
+{
+  if (!A) return set_error(B200_ERR_ARG, "null handle");
+  if (A->T) return B200_OK;
+  const int m = A->m, n = A->n, nz = A->nz;
+  std::vector<int>    ai((size_t)m + 1), aj((size_t)nz), ti((size_t)n + 1, 0), tj((size_t)nz);
+  std::vector<double> aa((size_t)nz), ta((size_t)nz);
+  B200_CUDA_TRY(cudaMemcpy(ai.data(), A->d_ai, ai.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  if (nz) {
+    B200_CUDA_TRY(cudaMemcpy(aj.data(), A->d_aj, (size_t)nz * sizeof(int), cudaMemcpyDeviceToHost));
+    B200_CUDA_TRY(cudaMemcpy(aa.data(), A->d_aa, (size_t)nz * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  // counting sort by column; rows are visited in ascending order so each column keeps it
+  for (int k = 0; k < nz; ++k) {
+    if (aj[k] < 0 || aj[k] >= n) return set_error(B200_ERR_ARG, "column index %d out of range [0,%d)", aj[k], n);
+    ti[aj[k] + 1]++;
+  }
+  for (int c = 0; c < n; ++c) ti[c + 1] += ti[c];
+  {
+    std::vector<int> next(ti.begin(), ti.end() - 1);
+    for (int i = 0; i < m; ++i)
+      for (int k = ai[i]; k < ai[i + 1]; ++k) {
+        int p = next[aj[k]]++;
+        tj[p] = i;
+        ta[p] = aa[k];
+      }
+  }
+  b200_csr_t T = nullptr;
+  B200_TRY(b200_csr_create(&T, n, m, ti.data(), tj.data(), ta.data()));
+  A->T = T;
+  return B200_OK;
+}
+
+static int transpose_common(b200_csr_s *A, const double *d_x, const double *d_z, double *d_y,
+                            int mode, cudaStream_t st)
+{
+  B200_TRY(check_mode(mode));
+  if (A->n == 0) return B200_OK;
+  const bool atomic = (mode == B200_MODE_FAST) && !A->T && env_int("B200_TRANSPOSE_ATOMIC", 0);
+  if (!atomic) {
+    B200_TRY(b200_csr_build_transpose(A));
+    if (d_z) return spmv_dispatch<true>(A->T, d_x, d_z, d_y, mode, st);
+    return spmv_dispatch<false>(A->T, d_x, nullptr, d_y, mode, st);
+  }
+  if (d_z) {
+    if (d_z != d_y)
+      B200_LAUNCH(k_copy, std::max(1, std::min(sm_count() * 8, (A->n + 255) / 256)), 256, 0, st, d_y, d_z, (long long)A->n);
+  } else {
+    B200_CUDA_TRY(cudaMemsetAsync(d_y, 0, (size_t)A->n * sizeof(double), st));
+  }
+  if (A->m) {
+    const long long thr = (long long)A->m * 4;
+    B200_LAUNCH((k_tr_atomic<4>), (unsigned)((thr + 255) / 256), 256, 0, st, A->m, A->d_ai, A->d_aj, A->d_aa, d_x, d_y);
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_spmv_transpose(b200_csr_t A, const double *d_x, double *d_y, int mode, void *stream)
+{
+  if (!A || (!d_x && A->m) || (!d_y && A->n)) return set_error(B200_ERR_ARG, "b200_spmv_transpose: null argument");
+  return transpose_common(A, d_x, nullptr, d_y, mode, (cudaStream_t)stream);
+}
+
+extern "C" int b200_spmv_transpose_add(b200_csr_t A, const double *d_x, const double *d_z,
+                                       double *d_y, int mode, void *stream)
+{
+  if (!A || (!d_x && A->m) || ((!d_y || !d_z) && A->n)) return set_error(B200_ERR_ARG, "b200_spmv_transpose_add: null argument");
+  return transpose_common(A, d_x, d_z, d_y, mode, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-vector entry points: what MatMult_SeqAIJ(Mat,Vec,Vec) does with PETSc 3.7.6 host Vecs.
+// ---------------------------------------------------------------------------------------------
+static int host_scratch(b200_csr_s *A, size_t nx, size_t ny)
+{
+  if (A->hx_len < nx) {
+    cudaFree(A->d_hx); A->d_hx = nullptr;
+    B200_CUDA_TRY(cudaMalloc((void **)&A->d_hx, std::max<size_t>(nx, 1) * sizeof(double)));
+    A->hx_len = nx;
+  }
+  if (A->hy_len < ny) {
+    cudaFree(A->d_hy); A->d_hy = nullptr;
+    B200_CUDA_TRY(cudaMalloc((void **)&A->d_hy, std::max<size_t>(ny, 1) * sizeof(double)));
+    A->hy_len = ny;
+  }
+  for (auto &s : A->hs) if (!s) B200_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  for (auto &e : A->hev) if (!e) B200_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return B200_OK;
+}
+
+extern "C" int b200_spmv_host(b200_csr_t A, const double *h_x, double *h_y, int mode)
+{
+  if (!A || (!h_x && A->n) || (!h_y && A->m)) return set_error(B200_ERR_ARG, "b200_spmv_host: null argument");
+  B200_TRY(check_mode(mode));
+  B200_TRY(host_scratch(A, A->n, A->m));
+  cudaStream_t s = A->hs[0];
+  B200_CUDA_TRY(cudaMemcpyAsync(A->d_hx, h_x, (size_t)A->n * sizeof(double), cudaMemcpyHostToDevice, s));
+  B200_TRY(spmv_dispatch<false>(A, A->d_hx, nullptr, A->d_hy, mode, s));
+  B200_CUDA_TRY(cudaMemcpyAsync(h_y, A->d_hy, (size_t)A->m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  B200_CUDA_TRY(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+extern "C" int b200_spmv_add_host(b200_csr_t A, const double *h_x, const double *h_y, double *h_z, int mode)
+{
+  if (!A || (!h_x && A->n) || ((!h_y || !h_z) && A->m)) return set_error(B200_ERR_ARG, "b200_spmv_add_host: null argument");
+  B200_TRY(check_mode(mode));
+  B200_TRY(host_scratch(A, A->n, A->m));
+  cudaStream_t s = A->hs[0];
+  B200_CUDA_TRY(cudaMemcpyAsync(A->d_hx, h_x, (size_t)A->n * sizeof(double), cudaMemcpyHostToDevice, s));
+  B200_CUDA_TRY(cudaMemcpyAsync(A->d_hy, h_y, (size_t)A->m * sizeof(double), cudaMemcpyHostToDevice, s));
+  B200_TRY(spmv_dispatch<true>(A, A->d_hx, A->d_hy, A->d_hy, mode, s));
+  B200_CUDA_TRY(cudaMemcpyAsync(h_z, A->d_hy, (size_t)A->m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  B200_CUDA_TRY(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+extern "C" int b200_spmv_transpose_host(b200_csr_t A, const double *h_x, double *h_y, int mode)
+{
+  if (!A || (!h_x && A->m) || (!h_y && A->n)) return set_error(B200_ERR_ARG, "b200_spmv_transpose_host: null argument");
+  B200_TRY(check_mode(mode));
+  B200_TRY(host_scratch(A, A->m, A->n));
+  cudaStream_t s = A->hs[0];
+  B200_CUDA_TRY(cudaMemcpyAsync(A->d_hx, h_x, (size_t)A->m * sizeof(double), cudaMemcpyHostToDevice, s));
+  B200_TRY(transpose_common(A, A->d_hx, nullptr, A->d_hy, mode, s));
+  B200_CUDA_TRY(cudaMemcpyAsync(h_y, A->d_hy, (size_t)A->n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  B200_CUDA_TRY(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+extern "C" int b200_host_alloc(void **p, size_t bytes)
+{
+  if (!p) return set_error(B200_ERR_ARG, "null pointer");
+  B200_TRY(ensure_device());
+  B200_CUDA_TRY(cudaHostAlloc(p, std::max<size_t>(bytes, 1), cudaHostAllocDefault));
+  return B200_OK;
+}
+extern "C" int b200_host_free(void *p)
+{
+  if (p) B200_CUDA_TRY(cudaFreeHost(p));
+  return B200_OK;
+}
+extern "C" int b200_host_register(void *p, size_t bytes)
+{
+  B200_TRY(ensure_device());
+  B200_CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return B200_OK;
+}
+extern "C" int b200_host_unregister(void *p)
+{
+  B200_CUDA_TRY(cudaHostUnregister(p));
+  return B200_OK;
+}
+
+// splitmix64 -> uniform [-1,1): the synthetic x of SURVEY 8(d)
+extern "C" int b200_gen_vector(double *h_x, int64_t n, uint64_t seed)
+{
+  if (!h_x && n) return set_error(B200_ERR_ARG, "null pointer");
+  for (int64_t i = 0; i < n; ++i) {
+    uint64_t z = (seed ^ (uint64_t)i) + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    h_x[i] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+  }
+  return B200_OK;
+}

@@ -1,0 +1,197 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars (north star):
+  * EXACT / EXACT_FMA modes: bit-exact against oracle.matmult / matmult(fma=True);
+  * FAST mode: |y - y_ref| <= 1e-13 * sum_j |a_ij x_j| per row;
+  * integer work (plans, compressed-row index) bit-exact.
+"""
+import numpy as np
+import pytest
+
+import gen
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-13
+
+
+def _dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _run(pk, torch, A, x, mode, kernel=None, add=None):
+    if kernel is not None:
+        A.set_kernel(kernel)
+    dx = _dev(torch, x)
+    dy = torch.full((A.m,), float("nan"), dtype=torch.float64, device="cuda")
+    if add is None:
+        A.mult(dx, dy, mode)
+    else:
+        A.mult_add(dx, _dev(torch, add), dy, mode)
+    torch.cuda.synchronize()
+    if kernel is not None:
+        A.set_kernel(pk.KERNEL_AUTO)
+    return dy.cpu().numpy()
+
+
+def _cases():
+    rng = np.random.default_rng(7)
+    cases = {}
+    p = oracle.poisson7(20)
+    cases["poisson7_20"] = (p["ai"], p["aj"], p["aa"], 20 ** 3)
+    p = oracle.poisson7(50)
+    cases["poisson7_50"] = (p["ai"], p["aj"], p["aa"], 50 ** 3)
+    ai, aj, aa = gen.stencil27(16, seed=3)
+    cases["stencil27_16"] = (ai, aj, aa, 16 ** 3)
+    ai, aj, aa = gen.powerlaw(20000, lmax=3000)
+    cases["powerlaw_20k"] = (ai, aj, aa, 20000)
+    ai, aj, aa = gen.random_csr(1000, 700, 40, rng, empty_frac=0.3)
+    cases["random_ragged"] = (ai, aj, aa, 700)
+    ai, aj, aa = gen.random_csr(5000, 300, 3, rng, empty_frac=0.9)
+    cases["mostly_empty"] = (ai, aj, aa, 300)
+    cases["single_row"] = (np.array([0, 3], np.int32), np.array([0, 2, 4], np.int32), np.array([1.5, -2.0, 0.25]), 5)
+    cases["all_empty"] = (np.zeros(11, np.int32), np.zeros(0, np.int32), np.zeros(0), 4)
+    return cases
+
+
+CASES = _cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("fma", [False, True])
+def test_exact_modes_bit_exact(pk, cuda, name, fma):
+    ai, aj, aa, n = CASES[name]
+    x = gen.uniform_pm1(n, seed=0xB200)
+    ref = oracle.matmult(ai, aj, aa, x, fma=fma)
+    A = pk.Csr(ai, aj, aa, n=n)
+    mode = pk.MODE_EXACT_FMA if fma else pk.MODE_EXACT
+    info = A.info()
+    kernels = [None, pk.KERNEL_ROW]
+    if info.stream_tiles:
+        kernels.append(pk.KERNEL_STREAM)
+    if info.compressedrow_use:
+        kernels.append(pk.KERNEL_CPROW)
+    for k in kernels:
+        y = _run(pk, cuda, A, x, mode, kernel=k)
+        assert np.array_equal(y, ref), f"{name} kernel={k} fma={fma}: max diff {np.abs(y - ref).max()}"
+    A.destroy()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fast_mode_within_row_bound(pk, cuda, name):
+    ai, aj, aa, n = CASES[name]
+    x = gen.uniform_pm1(n, seed=0xB200)
+    ref = oracle.matmult(ai, aj, aa, x)
+    bound = TOL * oracle.row_abs_sum(ai, aj, aa, x)
+    A = pk.Csr(ai, aj, aa, n=n)
+    info = A.info()
+    kernels = [None, pk.KERNEL_ROW, pk.KERNEL_VECTOR]
+    if info.stream_tiles:
+        kernels.append(pk.KERNEL_STREAM)
+    for k in kernels:
+        y = _run(pk, cuda, A, x, pk.MODE_FAST, kernel=k)
+        assert np.all(np.abs(y - ref) <= bound), f"{name} kernel={k}: {np.max(np.abs(y - ref) - bound)}"
+    A.destroy()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_multadd_bit_exact(pk, cuda, name):
+    ai, aj, aa, n = CASES[name]
+    m = len(ai) - 1
+    x = gen.uniform_pm1(n, seed=1)
+    y0 = gen.uniform_pm1(m, seed=2)
+    y0[::7] = -0.0
+    ref = oracle.matmultadd(ai, aj, aa, x, y0)
+    A = pk.Csr(ai, aj, aa, n=n)
+    info = A.info()
+    kernels = [None, pk.KERNEL_ROW] + ([pk.KERNEL_STREAM] if info.stream_tiles else []) + (
+        [pk.KERNEL_CPROW] if info.compressedrow_use else [])
+    for k in kernels:
+        z = _run(pk, cuda, A, x, pk.MODE_EXACT, kernel=k, add=y0)
+        assert np.array_equal(z, ref), f"{name} kernel={k}"
+        assert np.array_equal(np.signbit(z), np.signbit(ref))
+    # in place (z aliases y), the MatMult_MPIAIJ use: yy = B*lvec + yy
+    dx = cuda.from_numpy(x).cuda()
+    dy = cuda.from_numpy(y0.copy()).cuda()
+    A.mult_add(dx, dy, dy, pk.MODE_EXACT)
+    assert np.array_equal(dy.cpu().numpy(), ref)
+    A.destroy()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_transpose(pk, cuda, name):
+    ai, aj, aa, n = CASES[name]
+    m = len(ai) - 1
+    x = gen.uniform_pm1(m, seed=5)
+    A = pk.Csr(ai, aj, aa, n=n)
+    dx = cuda.from_numpy(x).cuda()
+    dy = cuda.full((n,), float("nan"), dtype=cuda.float64, device="cuda")
+    ref = oracle.matmulttranspose(ai, aj, aa, x, n)
+    A.mult_transpose(dx, dy, pk.MODE_EXACT)
+    assert np.array_equal(dy.cpu().numpy(), ref)
+    ref_f = oracle.matmulttranspose(ai, aj, aa, x, n, fma=True)
+    A.mult_transpose(dx, dy, pk.MODE_EXACT_FMA)
+    assert np.array_equal(dy.cpu().numpy(), ref_f)
+    # transpose-add
+    z = gen.uniform_pm1(n, seed=6)
+    refa = oracle.matmulttransposeadd(ai, aj, aa, x, z, n)
+    dz = cuda.from_numpy(z).cuda()
+    A.mult_transpose_add(dx, dz, dy, pk.MODE_EXACT)
+    assert np.array_equal(dy.cpu().numpy(), refa)
+    # fast mode within the column bound
+    A.mult_transpose(dx, dy, pk.MODE_FAST)
+    absb = np.zeros(n)
+    np.add.at(absb, aj, np.abs(aa * np.repeat(x, np.diff(ai))))
+    assert np.all(np.abs(dy.cpu().numpy() - ref) <= TOL * absb)
+    A.destroy()
+
+
+def test_host_vector_entry(pk, cuda):
+    p = oracle.poisson7(30)
+    A = pk.Csr(p["ai"], p["aj"], p["aa"])
+    x = gen.uniform_pm1(A.n)
+    y = A.mult_host(x, mode=pk.MODE_EXACT)
+    assert np.array_equal(y, oracle.matmult(p["ai"], p["aj"], p["aa"], x))
+    y0 = gen.uniform_pm1(A.m, seed=9)
+    z = A.mult_add_host(x, y0, mode=pk.MODE_EXACT)
+    assert np.array_equal(z, oracle.matmultadd(p["ai"], p["aj"], p["aa"], x, y0))
+    yt = A.mult_transpose_host(x, mode=pk.MODE_EXACT)
+    assert np.array_equal(yt, oracle.matmulttranspose(p["ai"], p["aj"], p["aa"], x, A.n))
+    A.destroy()
+
+
+def test_plan_integers(pk, cuda):
+    """compressed-row verdict and statistics are bit-exact against the oracle's restatement."""
+    rng = np.random.default_rng(11)
+    for empty in (0.0, 0.5, 0.61, 0.95):
+        ai, aj, aa = gen.random_csr(2000, 500, 5, rng, empty_frac=empty)
+        A = pk.Csr(ai, aj, aa, n=500)
+        info = A.info()
+        lens = np.diff(ai)
+        assert info.nonzerorowcnt == int((lens > 0).sum())
+        assert info.rmax == int(lens.max())
+        use, cpi, ridx = oracle.check_compressed_row(ai, info.nonzerorowcnt)
+        assert bool(info.compressedrow_use) == use
+        if use:
+            assert info.cprow_nrows == len(ridx)
+        A.destroy()
+
+
+def test_update_values(pk, cuda):
+    p = oracle.poisson7(12)
+    A = pk.Csr(p["ai"], p["aj"], p["aa"])
+    aa2 = p["aa"] * 0.5 + 1.0
+    A.update_values(aa2)
+    x = gen.uniform_pm1(A.n)
+    assert np.array_equal(A.mult_host(x, mode=pk.MODE_EXACT), oracle.matmult(p["ai"], p["aj"], aa2, x))
+    A.destroy()
+
+
+def test_launches_counted(pk, cuda):
+    p = oracle.poisson7(10)
+    A = pk.Csr(p["ai"], p["aj"], p["aa"])
+    l0 = pk.launch_count()
+    A.mult_host(gen.uniform_pm1(A.n))
+    assert pk.launch_count() > l0
+    A.destroy()
