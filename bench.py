@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- MatMult throughput of the SeqAIJ hot path on the 300^3 7-point Poisson matrix.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid 300]
+
+A "step" is one MatMult (y = A x) over the whole matrix: 188,460,000 non-zeros, 27,000,000 rows,
+fp64 values, int32 indices -- BASELINE.json configs[1].  At N > 1 (torchrun, one rank per GPU) the
+same matrix is row-partitioned like MatMult_MPIAIJ (configs[2]): strong scaling.
+
+One JSON line on rank 0:
+  value     whole-job algorithmic GB/s, (nnz*12 + rows*20) bytes per MatMult / device time,
+            x and y resident in HBM;
+  e2e       the same metric through the host-vector entry point (what MatMult_SeqAIJ(Mat,Vec,Vec)
+            sees with PETSc 3.7.6 host Vecs): pinned-host x uploaded and y downloaded every step;
+  roofline  achieved GB/s of the dominant kernel against MEASURED_PEAKS.json's copy bandwidth;
+  cpu_baseline  the oracle (CPU restatement of the reference kernel) on the box's host cores.
+--impl reference times that CPU kernel as the arm to compare against.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MatMult GB/s (% of HBM roofline) & GFLOP/s, 300^3 Poisson fp64, 1/2/4/8 B200"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def algorithmic_bytes(nnz, rows):
+    """nnz*(8+4) + rows*(4+8+8), independent of the storage format."""
+    return nnz * 12 + rows * 20
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.002):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period, self.index = period, index
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        for k in dir(nv):
+            if k.startswith("nvmlClocksThrottleReason") or k.startswith("nvmlClocksEventReason"):
+                v = getattr(nv, k)
+                if isinstance(v, int) and v:
+                    names.setdefault(v, k.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", ""))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit and nm not in ("None", "All"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        # GpuIdle / ApplicationsClocksSetting are not throttles
+        benign = {"GpuIdle", "ApplicationsClocksSetting"}
+        rs = sorted(x for x in self.reasons if x not in benign)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": rs, "samples": len(self.samples)}
+
+
+def gen_poisson(pk, n, size=1, rank=0):
+    out = np.zeros(12, np.int32)
+    pk.check(pk.lib.b200_gen_poisson7_info(n, n, n, size, rank, out.ctypes.data_as(C.c_void_p)))
+    nloc, rstart, nnz = int(out[9]), int(out[10]), int(out[11])
+    ai = np.zeros(nloc + 1, np.int32)
+    aj = np.zeros(nnz, np.int32)
+    aa = np.zeros(nnz)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    pk.check(pk.lib.b200_gen_poisson7(n, n, n, size, rank, 1, p(ai), p(aj), p(aa), None, None))
+    return ai, aj, aa, rstart
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """The reference's CPU MatMult_SeqAIJ loop (oracle restatement: PETSc cannot be built offline
+    here), one contiguous row block per host thread ~ one MPI rank per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    import petsc_openacc_b200 as pk  # generator only (host code); no GPU work on this arm
+    n = args.grid
+    ai, aj, aa, _ = gen_poisson(pk, n)
+    m, nnz = len(ai) - 1, len(aj)
+    x = pk.gen_vector(m, 0xB200)
+    y = np.empty(m)
+    cores = host_threads()
+    for _ in range(max(args.warmup, 1)):
+        oracle.matmult_mt(ai, aj, aa, x, cores, y=y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.matmult_mt(ai, aj, aa, x, cores, y=y)
+    dt = (time.perf_counter() - t0) / args.steps
+    gbs = algorithmic_bytes(nnz, m) / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "gflops": 2.0 * nnz / dt / 1e9,
+        "config": {"workload": f"3D Poisson 7-point {n}^3 fp64 MatMult_SeqAIJ, CPU host threads",
+                   "rows": m, "nnz": nnz, "algorithmic_bytes": algorithmic_bytes(nnz, m)},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full {n}^3 MatMults, one nnz-balanced row block per thread"},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline(ai, aj, aa, x, n):
+    import oracle
+    cores = host_threads()
+    m, nnz = len(ai) - 1, len(aj)
+    y = np.empty(m)
+    oracle.matmult_mt(ai, aj, aa, x, cores, y=y)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 10 or (time.perf_counter() - t0 < 2.0 and reps < 200):
+        oracle.matmult_mt(ai, aj, aa, x, cores, y=y)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": algorithmic_bytes(nnz, m) / dt / 1e9, "unit": "GB/s", "cores": cores,
+            "kind": "port", "ms_per_matmult": dt * 1e3,
+            "sample": f"{reps} full {n}^3 MatMults (oracle/seqaij_oracle.c orc_matmult_mt), one row block per thread"}, y
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import petsc_openacc_b200 as pk
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torchrun (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    pk.init(local)
+    if world > 1:
+        import bench_mpiaij
+        return bench_mpiaij.run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler)
+
+    n = args.grid
+    ai, aj, aa, _ = gen_poisson(pk, n)
+    m, nnz = len(ai) - 1, len(aj)
+    nbytes = algorithmic_bytes(nnz, m)
+    A = pk.Csr(ai, aj, aa)
+    info = A.info()
+    mode = {"fast": pk.MODE_FAST, "exact": pk.MODE_EXACT, "exact_fma": pk.MODE_EXACT_FMA}[args.mode]
+    hx = pk.PinnedArray(m)
+    hy = pk.PinnedArray(m)
+    hx.array[:] = pk.gen_vector(m, 0xB200)
+    x = torch.from_numpy(hx.array).cuda()
+    y = torch.zeros(m, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    # ---- device-resident throughput --------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        A.mult(x, y, mode)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = pk.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    for k in range(args.steps):
+        A.mult(x, y, mode, stream)
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize()
+    launches = pk.launch_count() - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)])
+    ms = total_ms / args.steps
+    value = nbytes / ms / 1e6
+
+    # ---- end to end through the host-vector entry (H2D x + kernel + D2H y every step) -------
+    e2e_steps = max(5, min(args.steps, 30))
+    for _ in range(2):
+        A.mult_host(hx.array, hy.array, mode)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        A.mult_host(hx.array, hy.array, mode)
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    clocks = sampler.stop()
+    y_host = hy.array.copy()
+    assert np.array_equal(y_host, y.cpu().numpy()), "host-vector path and device path disagree"
+
+    peak, peak_src = measured_peak()
+    kname = pk.KERNEL_NAMES[info.kernel_fast if mode == pk.MODE_FAST else info.kernel_exact]
+    kernel_ms = float(np.median(per))
+    roof = {"bound": "hbm", "achieved": nbytes / kernel_ms / 1e6, "peak": peak, "unit": "GB/s",
+            "frac": nbytes / kernel_ms / 1e6 / peak, "traffic": ncu_traffic(),
+            "kernel": f"k_{kname}", "kernel_ms_median": kernel_ms, "peak_source": peak_src,
+            "frac_of_nominal_8000": nbytes / kernel_ms / 1e6 / 8000.0}
+    cpu, y_cpu = cpu_baseline(ai, aj, aa, hx.array, n)
+    # parity of the timed result against the oracle, reported (the tests are the gate)
+    if mode == pk.MODE_EXACT:
+        parity = "bit-exact" if np.array_equal(y_cpu, y_host) else "MISMATCH"
+    else:
+        import oracle
+        bound = 1e-13 * oracle.row_abs_sum(ai, aj, aa, hx.array)
+        parity = "within 1e-13 row bound" if np.all(np.abs(y_cpu - y_host) <= bound) else "MISMATCH"
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "gflops": 2.0 * nnz / ms / 1e6,
+        "config": {"workload": f"3D Poisson 7-point {n}^3 fp64 MatMult_SeqAIJ on 1xB200 (BASELINE configs[1])",
+                   "rows": m, "nnz": nnz, "algorithmic_bytes": nbytes, "mode": args.mode,
+                   "kernel": f"k_{kname}", "l2": "inputs (2.8 GB) larger than the 126 MB L2; no flush",
+                   "parity_vs_oracle": parity},
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": nbytes / e2e_ms / 1e6, "unit": "GB/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": m * 8, "d2h_bytes_per_step": m * 8, "steps": e2e_steps,
+                "api": "b200_spmv_host (MatMult_SeqAIJ with host Vecs, pinned)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    A.destroy()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=300)
+    ap.add_argument("--mode", default="exact", choices=["fast", "exact", "exact_fma"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -396,7 +396,7 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
   if (threads != 128 && threads != 256) threads = 256;
   int cap = env_int("B200_STREAM_CAP", 0);
   if (cap <= 0) {
-    cap = (int)(threads * std::max(mean, 1.0) * 1.125) + 64;
+    cap = (int)(threads * std::max(mean, 1.0) * 1.05) + 32;
     cap = std::min(cap, 8192);
   }
   cap = std::max((cap + 3) & ~3, 64);
@@ -419,13 +419,12 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
     }
     if (stream_ok) {
       const size_t sbytes = stream_stage_bytes(threads, cap);
-      if (stages <= 0) {
-        // two CTAs per SM, as many stages as fit under ~110 KB per CTA
-        stages = (int)std::min<size_t>(8, std::max<size_t>(2, (110 * 1024 - 128) / sbytes));
-      }
-      stages = std::min(std::max(stages, 2), 8);
+      // Measured on B200 (profiles/r01_sweep_*.log): throughput follows the number of resident
+      // consumer threads (the x gather is latency bound), so prefer a short ring and many CTAs.
+      if (stages <= 0) stages = 2;
+      stages = std::min(std::max(stages, 1), 8);
       A->stream_smem = 128 + (size_t)stages * sbytes;
-      if (A->stream_smem > 227 * 1024) { stages = 2; A->stream_smem = 128 + 2 * sbytes; }
+      if (A->stream_smem > 227 * 1024) { stages = 1; A->stream_smem = 128 + sbytes; }
       if (A->stream_smem > 227 * 1024) stream_ok = false;
     }
     if (stream_ok) {

@@ -76,9 +76,9 @@ def main():
     A.destroy()
     mean = nz / m
     for threads in (256, 128):
-        for capmul in (1.0, 2.0):
-            for stages in (2, 3, 4, 6):
-                for ctas in (1, 2, 3, 4):
+        for capmul in (1.0,):
+            for stages in (1, 2, 3):
+                for ctas in (2, 4, 6, 8, 12):
                     cap = int(threads * mean * capmul * 1.05) + 32
                     os.environ.update(B200_STREAM_THREADS=str(threads), B200_STREAM_CAP=str(cap),
                                       B200_STREAM_STAGES=str(stages), B200_STREAM_CTAS_PER_SM=str(ctas))

@@ -1,0 +1,58 @@
+"""The C-ABI library loads, exports every symbol include/*.h declares, and refuses to compute
+without a GPU (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for fn in sorted(os.listdir(inc)):
+        if not fn.endswith(".h"):
+            continue
+        text = open(os.path.join(inc, fn)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", text):
+            if m.group(1) not in ("defined",):
+                names.add((fn, m.group(1)))
+    return names
+
+
+def test_every_declared_symbol_is_exported(pk):
+    libs = {"b200_seqaij.h": pk.lib}
+    host = os.path.join(ROOT, "petsc-openacc_b200", "libb200petsc.so")
+    if os.path.exists(host):
+        libs["b200_petsc_symbols.h"] = C.CDLL(host)
+    decl = declared_symbols()
+    assert len([1 for f, _ in decl if f == "b200_seqaij.h"]) >= 30
+    for fn, name in sorted(decl):
+        lib = libs.get(fn)
+        assert lib is not None, f"no library built for {fn}"
+        assert hasattr(lib, name), f"{name} declared in include/{fn} is not exported"
+    assert set(pk.ABI_SYMBOLS) <= {n for _, n in decl}
+
+
+def test_no_cpu_fallback(pk):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ai = np.array([0, 1], np.int32)
+    with pytest.raises(pk.B200Error) as e:
+        pk.Csr(ai, np.array([0], np.int32), np.array([1.0]))
+    assert e.value.code == 92 and "no CPU fallback" in str(e.value)
+    out = np.zeros(1)
+    rc = pk.lib.b200_vec_dot(None, None, C.c_int64(0), out.ctypes.data_as(C.c_void_p), None)
+    assert rc == 92
+
+
+def test_argument_errors_do_not_abort(pk):
+    assert pk.lib.b200_csr_create(None, 1, 1, None, None, None) == 60
+    assert pk.lib.b200_spmv(None, None, None, 0, None) == 60
+    assert pk.lib.b200_csr_destroy(None) == 0
+    assert b"b200" in pk.lib.b200_version()

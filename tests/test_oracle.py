@@ -1,0 +1,209 @@
+"""CPU tests of the oracle: against the committed golden checksums, against independent
+restatements (numpy / scipy), and against the reference's only known-answer test (the analytic
+solution of src/main_ksp.cpp:5-15,120-121)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spl
+
+import gen
+import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "poisson7.json")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("case", GOLD["seq"], ids=lambda c: f"N{c['N']}")
+def test_golden_seq(case):
+    N = case["N"]
+    p = oracle.poisson7(N)
+    assert int(p["ai"][-1]) == case["nnz"] == 7 * N ** 3 - 6 * N ** 2
+    for k in ("ai", "aj", "aa", "rhs", "exact"):
+        assert sha(p[k]) == case[k], k
+    assert p["scale"].hex() == case["scale"]
+    x = gen.uniform_pm1(N ** 3, seed=0xB200)
+    assert sha(oracle.matmult(p["ai"], p["aj"], p["aa"], x)) == case["y_rand"]
+    assert sha(oracle.matmult(p["ai"], p["aj"], p["aa"], x, fma=True)) == case["y_rand_fma"]
+    assert sha(oracle.matmult(p["ai"], p["aj"], p["aa"], p["exact"])) == case["y_exact"]
+    assert sha(oracle.matmulttranspose(p["ai"], p["aj"], p["aa"], x, N ** 3)) == case["yt_rand"]
+
+
+@pytest.mark.parametrize("case", GOLD["mpi"], ids=lambda c: f"N{c['N']}x{c['size']}")
+def test_golden_mpi(case):
+    N, size = case["N"], case["size"]
+    assert list(oracle.dmda_decide(N, N, N, size)) == case["grid"]
+    base = oracle.dmda_bases(N, N, N, size)
+    assert [int(b) for b in base] == case["bases"]
+    for r, g in enumerate(case["ranks"]):
+        p = oracle.poisson7(N, size=size, rank=r)
+        (Ai, Aj, Aa), (Bi, Bj, Ba) = oracle.mpiaij_split(p["ai"], p["aj"], p["aa"], p["rstart"], p["rend"])
+        Bjc, garray = oracle.mpiaij_setup_multiply(Bj)
+        assert (len(Aj), len(Bj), len(garray)) == (g["A_nnz"], g["B_nnz"], g["nghost"])
+        for k, v in (("Ai", Ai), ("Aj", Aj), ("Aa", Aa), ("Bi", Bi), ("Bj", Bjc), ("Ba", Ba), ("garray", garray)):
+            assert sha(v) == g[k], k
+        assert [int(v) for v in oracle.scatter_recv_offsets(base, garray)] == g["recv_off"]
+
+
+def test_survey_sizes():
+    """process grids and the 300^3 value 1/(dx*dx) = 89999.99999999999."""
+    for s, g in GOLD["decide_300"].items():
+        assert list(oracle.dmda_decide(300, 300, 300, int(s))) == g
+    assert 1.0 / ((1.0 / 300) * (1.0 / 300)) == 89999.99999999999
+    # 8-rank layout of a 30^3 grid scales like the survey's 300^3 numbers (faces 3*15^2 etc.)
+    p = oracle.poisson7(30, size=8, rank=0)
+    (Ai, Aj, Aa), (Bi, Bj, Ba) = oracle.mpiaij_split(p["ai"], p["aj"], p["aa"], p["rstart"], p["rend"])
+    Bjc, garray = oracle.mpiaij_setup_multiply(Bj)
+    assert len(garray) == 3 * 15 * 15 and len(Bj) == 3 * 15 * 15
+    assert int((np.diff(Bi) > 0).sum()) == 3 * 15 * 15 - 3 * 15 + 1
+    assert len(Aj) == 7 * 15 ** 3 - 6 * 15 ** 2
+
+
+@pytest.mark.parametrize("N", [3, 4, 7, 20])
+def test_generator_matches_numpy_restatement(N):
+    ai, aj, aa = gen.poisson7_natural(N)
+    p = oracle.poisson7(N)
+    assert np.array_equal(ai, p["ai"]) and np.array_equal(aj, p["aj"]) and np.array_equal(aa, p["aa"])
+
+
+def test_known_answer_analytic_solution():
+    """The reference's own check: the discrete solution converges to cos*cos*cos at O(h^2)."""
+    errs = []
+    for N in (8, 16, 32):
+        p = oracle.poisson7(N)
+        A = sp.csr_matrix((p["aa"], p["aj"], p["ai"]), shape=(N ** 3, N ** 3)).tocsc()
+        u = spl.spsolve(A, p["rhs"])
+        errs.append(np.abs(u - p["exact"]).max())
+    assert errs[0] > errs[1] > errs[2]
+    assert 3.0 < errs[0] / errs[1] < 5.0 and 3.0 < errs[1] / errs[2] < 5.0
+    assert errs[2] < 0.01
+
+
+def test_matmult_family_against_scipy_and_loops():
+    rng = np.random.default_rng(3)
+    for m, n, d, e in ((50, 40, 6, 0.2), (300, 300, 30, 0.0), (200, 10, 3, 0.8)):
+        ai, aj, aa = gen.random_csr(m, n, d, rng, empty_frac=e)
+        A = sp.csr_matrix((aa, aj, ai), shape=(m, n))
+        x, y0, xt = rng.uniform(-1, 1, n), rng.uniform(-1, 1, m), rng.uniform(-1, 1, m)
+        # python-loop restatement, strict left to right
+        ref = np.zeros(m)
+        for i in range(m):
+            s = 0.0
+            for k in range(ai[i], ai[i + 1]):
+                s += aa[k] * x[aj[k]]
+            ref[i] = s
+        assert np.array_equal(oracle.matmult(ai, aj, aa, x), ref)
+        np.testing.assert_allclose(oracle.matmult(ai, aj, aa, x), A @ x, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(oracle.matmult(ai, aj, aa, x, fma=True), ref, rtol=0, atol=1e-13)
+        refadd = np.zeros(m)
+        for i in range(m):
+            s = y0[i]
+            for k in range(ai[i], ai[i + 1]):
+                s += aa[k] * x[aj[k]]
+            refadd[i] = s
+        assert np.array_equal(oracle.matmultadd(ai, aj, aa, x, y0), refadd)
+        reft = np.zeros(n)
+        for i in range(m):
+            for k in range(ai[i], ai[i + 1]):
+                reft[aj[k]] += xt[i] * aa[k]
+        assert np.array_equal(oracle.matmulttranspose(ai, aj, aa, xt, n), reft)
+        z = rng.uniform(-1, 1, n)
+        refta = z.copy()
+        for i in range(m):
+            for k in range(ai[i], ai[i + 1]):
+                refta[aj[k]] += xt[i] * aa[k]
+        assert np.array_equal(oracle.matmulttransposeadd(ai, aj, aa, xt, z, n), refta)
+        # compressed-row variants give the same numbers as the plain ones
+        nzr = int((np.diff(ai) > 0).sum())
+        use, cpi, ridx = oracle.check_compressed_row(ai, nzr)
+        assert use == (m - nzr >= 0.6 * m)
+        if use:
+            assert np.array_equal(oracle.matmult_cprow(m, cpi, ridx, aj, aa, x), ref)
+            assert np.array_equal(oracle.matmultadd_cprow(m, cpi, ridx, aj, aa, x, y0), refadd)
+        assert oracle.matmult_flops(len(aj), nzr) == 2.0 * len(aj) - nzr
+
+
+def test_multithreaded_baseline_identical():
+    p = oracle.poisson7(20)
+    x = gen.uniform_pm1(20 ** 3)
+    ref = oracle.matmult(p["ai"], p["aj"], p["aa"], x)
+    for t in (1, 3, 8):
+        assert np.array_equal(oracle.matmult_mt(p["ai"], p["aj"], p["aa"], x, t), ref)
+
+
+def test_assembly_end_compaction():
+    """MatAssemblyEnd_SeqAIJ: rows stored with slack are packed; counters follow."""
+    rng = np.random.default_rng(5)
+    m = 200
+    imax = rng.integers(0, 9, size=m).astype(np.int32)
+    ailen = np.array([rng.integers(0, mx + 1) for mx in imax], dtype=np.int32)
+    ai = np.zeros(m + 1, dtype=np.int32)
+    np.cumsum(imax, out=ai[1:])
+    aj = np.full(ai[-1], -7, dtype=np.int32)
+    aa = np.full(ai[-1], np.nan)
+    rows = []
+    for i in range(m):
+        c = np.sort(rng.choice(1000, size=ailen[i], replace=False)).astype(np.int32)
+        v = rng.uniform(-1, 1, size=ailen[i])
+        aj[ai[i]:ai[i] + ailen[i]] = c
+        aa[ai[i]:ai[i] + ailen[i]] = v
+        rows.append((c, v))
+    unused = int(imax.sum() - ailen.sum())
+    nz, nzr, rmax, fshift = oracle.assembly_end(ai, aj, aa, imax, ailen)
+    assert nz == sum(len(c) for c, _ in rows) == ai[-1]
+    assert nzr == sum(len(c) > 0 for c, _ in rows)
+    assert rmax == max(len(c) for c, _ in rows)
+    assert fshift == unused
+    for i, (c, v) in enumerate(rows):
+        assert np.array_equal(aj[ai[i]:ai[i + 1]], c) and np.array_equal(aa[ai[i]:ai[i + 1]], v)
+    assert np.array_equal(imax, np.diff(ai)) and np.array_equal(ailen, np.diff(ai))
+
+
+def test_mpiaij_reassembles_to_sequential_operator():
+    """A x_local + B x_ghost over all ranks equals the 1-rank operator permuted to PETSc order."""
+    N, size = 10, 8
+    base = oracle.dmda_bases(N, N, N, size)
+    n = N ** 3
+    rng = np.random.default_rng(1)
+    xg = rng.uniform(-1, 1, n)  # in PETSc (rank-major) ordering
+    # natural -> PETSc ordering permutation
+    perm = np.zeros(n, dtype=np.int64)
+    for r in range(size):
+        inf = oracle.dmda_info(N, N, N, size, r)
+        idx = 0
+        for k in range(inf["zs"], inf["zs"] + inf["zm"]):
+            for j in range(inf["ys"], inf["ys"] + inf["ym"]):
+                for i in range(inf["xs"], inf["xs"] + inf["xm"]):
+                    perm[i + j * N + k * N * N] = base[r] + idx
+                    idx += 1
+    p1 = oracle.poisson7(N)
+    A1 = sp.csr_matrix((p1["aa"], p1["aj"], p1["ai"]), shape=(n, n))
+    xnat = xg[perm]
+    ynat = A1 @ xnat
+    for r in range(size):
+        p = oracle.poisson7(N, size=size, rank=r)
+        (Ai, Aj, Aa), (Bi, Bj, Ba) = oracle.mpiaij_split(p["ai"], p["aj"], p["aa"], p["rstart"], p["rend"])
+        Bjc, garray = oracle.mpiaij_setup_multiply(Bj)
+        assert np.all(np.diff(garray) > 0)
+        y = oracle.matmult(Ai, Aj, Aa, xg[p["rstart"]:p["rend"]])
+        y = oracle.matmultadd(Bi, Bjc, Ba, xg[garray], y)
+        inv = np.argsort(perm)  # PETSc index -> natural index
+        np.testing.assert_allclose(y, ynat[inv[p["rstart"]:p["rend"]]], rtol=0, atol=1e-9)
+        # rhs/exact are the same fields in the other ordering
+        assert np.array_equal(p["exact"], p1["exact"][inv[p["rstart"]:p["rend"]]])
+
+
+def test_cg_jacobi_solves_reference_problem():
+    p = oracle.poisson7(12)
+    x, its, rn = oracle.cg_jacobi(p["ai"], p["aj"], p["aa"], p["rhs"], rtol=1e-12, atol=1e-50)
+    assert its > 0
+    A = sp.csr_matrix((p["aa"], p["aj"], p["ai"]))
+    assert np.linalg.norm(A @ x - p["rhs"]) / np.linalg.norm(p["rhs"]) < 1e-9
+    assert np.abs(x - p["exact"]).max() < 0.06
