@@ -292,6 +292,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=300)
     ap.add_argument("--mode", default="exact", choices=["fast", "exact", "exact_fma"])
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

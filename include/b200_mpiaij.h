@@ -1,0 +1,86 @@
+/*
+ * b200_mpiaij.h -- C ABI of the row-partitioned mat-vec (MatMult_MPIAIJ) for one box of B200s.
+ *
+ * What it replaces (PETSc 3.7.6, un-vendored, reached from the reference through
+ * DMSetMatType(da, MATAIJ) on PETSC_COMM_WORLD, src/helper.cpp:31,39, with aprun -n > 1,
+ * runs/single-node-scaling.pbs:60):
+ *     Mat_MPIAIJ {A, B, garray, lvec, Mvctx}          mpiaij.h
+ *     MatSetValues_MPIAIJ's diagonal / off-diagonal split
+ *     MatSetUpMultiply_MPIAIJ                          mmaij.c   (garray, B column compaction)
+ *     MatMult_MPIAIJ                                   mpiaij.c  (scatter begin, A x, scatter end,
+ *                                                                  y += B lvec)
+ *     VecScatter (MPI persistent sends/recvs on host)  vscat.c
+ * One process per GPU.  The halo exchange is push based: the sending rank's pack kernel stores its
+ * boundary x values straight into the receiving rank's lvec over NVLink (CUDA IPC mapping) and
+ * then releases a per-source flag; the receiving rank's off-diagonal kernel acquires the flags.
+ * No host round trip, no receive-side copy, and the transfer overlaps A x by construction.
+ *
+ * Process plumbing (who is rank r, exchanging the 64-byte IPC handles and the garray lists) is the
+ * caller's: bench.py / tests use torch.distributed for it.  Everything returns 0 or a b200 error.
+ */
+#ifndef B200_MPIAIJ_H
+#define B200_MPIAIJ_H
+
+#include "b200_seqaij.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_mpiaij_s *b200_mpiaij_t;
+
+/* Host-side construction (no GPU needed): rows [base[rank], base[rank+1]) of the global matrix
+ * with GLOBAL column ids ascending in each row.  Splits into A (columns owned by this rank,
+ * local ids) and B (the rest), builds garray = sorted unique ghost ids, rewrites B's columns to
+ * positions in garray, and the receive offsets per owner rank. */
+int b200_mpiaij_create(b200_mpiaij_t *out, int32_t size, int32_t rank, const int32_t *base,
+                       const int32_t *h_ai, const int32_t *h_aj_global, const double *h_aa);
+int b200_mpiaij_destroy(b200_mpiaij_t M);
+
+/* sizes[6] = nloc, nnz(A), nnz(B), nghost, non-empty rows of B, number of source ranks */
+int b200_mpiaij_get_sizes(b200_mpiaij_t M, int32_t *sizes);
+int b200_mpiaij_get_garray(b200_mpiaij_t M, int32_t *garray);
+int b200_mpiaij_get_recv_offsets(b200_mpiaij_t M, int32_t *off /* size+1 */);
+/* host copies of a block: which = 0 (A) or 1 (B, compact columns); any pointer may be NULL */
+int b200_mpiaij_copy_block(b200_mpiaij_t M, int which, int32_t *ai, int32_t *aj, double *aa);
+
+/* Tell this rank what `peer` needs: peer's garray (ascending global ids).  The send list is the
+ * run of ids inside this rank's ownership range, in that order (VecScatter's convention), landing
+ * at lvec offset = position of the run in peer's garray. */
+int b200_mpiaij_set_peer_garray(b200_mpiaij_t M, int32_t peer, const int32_t *peer_garray,
+                                int32_t peer_nghost);
+/* the resulting send list (local x indices) for tests; returns count through *count */
+int b200_mpiaij_get_send_list(b200_mpiaij_t M, int32_t peer, int32_t *count, int32_t *local_idx,
+                              int32_t *peer_offset);
+
+/* ---- device side ------------------------------------------------------------------------- */
+/* Upload A and B (kernel plans included) and allocate this rank's window:
+ * [lvec buffer 0][lvec buffer 1][flags: one uint64 per source rank][error word].            */
+int b200_mpiaij_upload(b200_mpiaij_t M);
+int b200_mpiaij_get_blocks(b200_mpiaij_t M, b200_csr_t *A, b200_csr_t *B); /* borrowed */
+int b200_mpiaij_window_ipc_handle(b200_mpiaij_t M, void *handle64);  /* cudaIpcMemHandle_t   */
+int b200_mpiaij_window_ptr(b200_mpiaij_t M, void **d_window);
+int b200_mpiaij_open_peer_window(b200_mpiaij_t M, int32_t peer, const void *handle64);
+int b200_mpiaij_set_peer_window(b200_mpiaij_t M, int32_t peer, void *d_window); /* same process */
+
+/* y = A x_local + B x_ghost.  begin = VecScatterBegin (pack + push + release flags),
+ * local = A x, end = VecScatterEnd + MatMultAdd (acquire flags, y += B lvec).
+ * b200_mpiaij_mult runs the three: push on an internal side stream, A then B on `stream`.     */
+int b200_mpiaij_mult_begin(b200_mpiaij_t M, const double *d_x, void *stream);
+int b200_mpiaij_mult_local(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream);
+int b200_mpiaij_mult_end(b200_mpiaij_t M, double *d_y, int mode, void *stream);
+int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream);
+/* The same with HOST vectors (PETSc 3.7.6 Vecs): this rank's x rows up, y rows down, synchronous. */
+int b200_mpiaij_mult_host(b200_mpiaij_t M, const double *h_x, double *h_y, int mode);
+/* Variant for a transport owned by the caller (NCCL send/recv through torch.distributed):
+ * pack boundary values for `peer` into d_buf, and y += B lvec from a caller-filled lvec.       */
+int b200_mpiaij_pack(b200_mpiaij_t M, int32_t peer, const double *d_x, double *d_buf, void *stream);
+int b200_mpiaij_mult_add_ghost(b200_mpiaij_t M, const double *d_lvec, double *d_y, int mode,
+                               void *stream);
+/* non-zero after a flag wait ran out of its spin budget (B200_MPIAIJ_TIMEOUT_MS, default 2000) */
+int b200_mpiaij_check(b200_mpiaij_t M);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_MPIAIJ_H */

@@ -162,6 +162,13 @@ int b200_cg_jacobi(b200_csr_t A, const double *d_b, double *d_x, double rtol, do
 /* ---- synthetic workloads (device-independent, counter based) ----------------- */
 /* uniform [-1,1) from splitmix64(seed ^ i) */
 int b200_gen_vector(double *h_x, int64_t n, uint64_t seed);
+/* The reference problem (src/helper.cpp:161-279: generateA + setRefPoint, :78-157 rhs/exact) for
+ * one rank of the DMDA decomposition PETSC_DECIDE picks for `size` ranks; PETSc ordering, global
+ * column ids ascending per row.  info[12] = m n p xs ys zs xm ym zm nloc rstart nnz.          */
+int b200_gen_poisson7_info(int M, int N, int P, int size, int rank, int32_t *info);
+int b200_gen_poisson7_bases(int M, int N, int P, int size, int32_t *base /* size+1 */);
+int b200_gen_poisson7(int M, int N, int P, int size, int rank, int refpoint, int32_t *ai,
+                      int32_t *aj_global, double *aa, double *rhs, double *exact);
 
 #ifdef __cplusplus
 }

@@ -277,3 +277,130 @@ def vec_copy(y, x, stream=None):
 def vec_pointwise_mult(w, x, y, stream=None):
     check(lib.b200_vec_pointwise_mult(_dptr(w), _dptr(x), _dptr(y), C.c_int64(x.numel()),
                                       _stream(stream)))
+
+
+# ---- MatMult_MPIAIJ (include/b200_mpiaij.h) ----------------------------------------------------
+MPIAIJ_SYMBOLS = [
+    "b200_mpiaij_create", "b200_mpiaij_destroy", "b200_mpiaij_get_sizes", "b200_mpiaij_get_garray",
+    "b200_mpiaij_get_recv_offsets", "b200_mpiaij_copy_block", "b200_mpiaij_set_peer_garray",
+    "b200_mpiaij_get_send_list", "b200_mpiaij_upload", "b200_mpiaij_get_blocks",
+    "b200_mpiaij_window_ipc_handle", "b200_mpiaij_window_ptr", "b200_mpiaij_open_peer_window",
+    "b200_mpiaij_set_peer_window", "b200_mpiaij_mult_begin", "b200_mpiaij_mult_local",
+    "b200_mpiaij_mult_end", "b200_mpiaij_mult", "b200_mpiaij_pack", "b200_mpiaij_mult_add_ghost",
+    "b200_mpiaij_check", "b200_mpiaij_mult_host",
+]
+ABI_SYMBOLS += MPIAIJ_SYMBOLS
+
+
+class MpiAij:
+    """One rank's Mat_MPIAIJ {A, B, garray, lvec}: host split + (after upload) device blocks."""
+
+    def __init__(self, size, rank, base, ai, aj_global, aa):
+        self.size, self.rank = int(size), int(rank)
+        self.base = np.ascontiguousarray(base, dtype=np.int32)
+        ai = np.ascontiguousarray(ai, dtype=np.int32)
+        aj = np.ascontiguousarray(aj_global, dtype=np.int32)
+        aa = np.ascontiguousarray(aa, dtype=np.float64)
+        self._h = C.c_void_p(0)
+        check(lib.b200_mpiaij_create(C.byref(self._h), C.c_int32(size), C.c_int32(rank),
+                                     _np_ptr(self.base), _np_ptr(ai), _np_ptr(aj), _np_ptr(aa)))
+        s = np.zeros(6, np.int32)
+        check(lib.b200_mpiaij_get_sizes(self._h, _np_ptr(s)))
+        self.nloc, self.annz, self.bnnz, self.nghost, self.brows, self.nsrc = (int(v) for v in s)
+
+    def destroy(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.b200_mpiaij_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def garray(self):
+        g = np.zeros(max(self.nghost, 1), np.int32)
+        check(lib.b200_mpiaij_get_garray(self._h, _np_ptr(g)))
+        return g[:self.nghost]
+
+    def recv_offsets(self):
+        off = np.zeros(self.size + 1, np.int32)
+        check(lib.b200_mpiaij_get_recv_offsets(self._h, _np_ptr(off)))
+        return off
+
+    def block(self, which):
+        nnz = self.bnnz if which else self.annz
+        ai = np.zeros(self.nloc + 1, np.int32)
+        aj = np.zeros(max(nnz, 1), np.int32)
+        aa = np.zeros(max(nnz, 1))
+        check(lib.b200_mpiaij_copy_block(self._h, C.c_int(which), _np_ptr(ai), _np_ptr(aj), _np_ptr(aa)))
+        return ai, aj[:nnz], aa[:nnz]
+
+    def set_peer_garray(self, peer, garray):
+        g = np.ascontiguousarray(garray, dtype=np.int32)
+        check(lib.b200_mpiaij_set_peer_garray(self._h, C.c_int32(peer), _np_ptr(g), C.c_int32(len(g))))
+
+    def send_list(self, peer):
+        cnt, off = C.c_int32(0), C.c_int32(0)
+        check(lib.b200_mpiaij_get_send_list(self._h, C.c_int32(peer), C.byref(cnt), None, C.byref(off)))
+        idx = np.zeros(max(cnt.value, 1), np.int32)
+        check(lib.b200_mpiaij_get_send_list(self._h, C.c_int32(peer), C.byref(cnt), _np_ptr(idx), C.byref(off)))
+        return idx[:cnt.value], off.value
+
+    def upload(self):
+        check(lib.b200_mpiaij_upload(self._h))
+
+    def ipc_handle(self):
+        buf = (C.c_ubyte * 64)()
+        check(lib.b200_mpiaij_window_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def window_ptr(self):
+        p = C.c_void_p(0)
+        check(lib.b200_mpiaij_window_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def open_peer_window(self, peer, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        check(lib.b200_mpiaij_open_peer_window(self._h, C.c_int32(peer), buf))
+
+    def set_peer_window(self, peer, ptr):
+        check(lib.b200_mpiaij_set_peer_window(self._h, C.c_int32(peer), C.c_void_p(ptr)))
+
+    def mult_begin(self, x, stream=None):
+        check(lib.b200_mpiaij_mult_begin(self._h, _dptr(x), _stream(stream)))
+
+    def mult_local(self, x, y, mode=MODE_FAST, stream=None):
+        check(lib.b200_mpiaij_mult_local(self._h, _dptr(x), _dptr(y), C.c_int(mode), _stream(stream)))
+
+    def mult_end(self, y, mode=MODE_FAST, stream=None):
+        check(lib.b200_mpiaij_mult_end(self._h, _dptr(y), C.c_int(mode), _stream(stream)))
+
+    def mult(self, x, y, mode=MODE_FAST, stream=None):
+        check(lib.b200_mpiaij_mult(self._h, _dptr(x), _dptr(y), C.c_int(mode), _stream(stream)))
+
+    def mult_host(self, hx, hy, mode=MODE_FAST):
+        check(lib.b200_mpiaij_mult_host(self._h, _np_ptr(hx), _np_ptr(hy), C.c_int(mode)))
+
+    def pack(self, peer, x, buf, stream=None):
+        check(lib.b200_mpiaij_pack(self._h, C.c_int32(peer), _dptr(x), _dptr(buf), _stream(stream)))
+
+    def mult_add_ghost(self, lvec, y, mode=MODE_FAST, stream=None):
+        check(lib.b200_mpiaij_mult_add_ghost(self._h, _dptr(lvec), _dptr(y), C.c_int(mode), _stream(stream)))
+
+    def check(self):
+        check(lib.b200_mpiaij_check(self._h))
+
+
+def gen_poisson7(M, size=1, rank=0, refpoint=True, vectors=False):
+    """This rank's rows of the reference problem (src/helper.cpp) from the product generator."""
+    out = np.zeros(12, np.int32)
+    check(lib.b200_gen_poisson7_info(M, M, M, size, rank, _np_ptr(out)))
+    nloc, rstart, nnz = int(out[9]), int(out[10]), int(out[11])
+    ai, aj, aa = np.zeros(nloc + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+    rhs = np.zeros(nloc) if vectors else None
+    ex = np.zeros(nloc) if vectors else None
+    check(lib.b200_gen_poisson7(M, M, M, size, rank, int(refpoint), _np_ptr(ai), _np_ptr(aj),
+                                _np_ptr(aa), _np_ptr(rhs) if vectors else None,
+                                _np_ptr(ex) if vectors else None))
+    base = np.zeros(size + 1, np.int32)
+    check(lib.b200_gen_poisson7_bases(M, M, M, size, _np_ptr(base)))
+    return dict(ai=ai, aj=aj, aa=aa, rhs=rhs, exact=ex, rstart=rstart, base=base, info=out)
+
+
+ABI_SYMBOLS += ["b200_gen_poisson7_info", "b200_gen_poisson7_bases", "b200_gen_poisson7"]

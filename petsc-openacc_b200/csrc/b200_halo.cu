@@ -1,0 +1,515 @@
+// b200_halo.cu -- MatMult_MPIAIJ for one box of B200s: A/B split, garray, scatter lists (host,
+// integer work bit-exact with MatSetUpMultiply_MPIAIJ's result) and a push-based NVLink halo.
+//
+// What it replaces [P376, un-vendored]: mpiaij.c MatMult_MPIAIJ, mmaij.c
+// MatSetUpMultiply_MPIAIJ, vscat.c VecScatterBegin/End (MPI persistent send/recv of HOST buffers;
+// SURVEY 3.4, 5.9).  Here rank r's pack kernel stores boundary x values directly into the peer's
+// lvec through a CUDA-IPC mapping (NVLink 5 / NVSwitch), fences, and releases a per-source flag
+// in the peer's window; the peer's off-diagonal kernel acquires the flags and adds B*lvec.
+//
+// Window layout (one cudaMalloc per rank, exported with cudaIpcGetMemHandle):
+//   [0, 1024)                      uint64 flags[size<=120] ; word 126 = error, word 127 = magic
+//   [1024, 1024 + 8*ngpad)         lvec buffer 0
+//   [.. + 8*ngpad, .. + 16*ngpad)  lvec buffer 1          (ngpad = nghost rounded up to 16)
+// Buffers alternate with the MatMult sequence number, which makes the exchange safe without a
+// reverse "buffer free" signal: a peer can only be one MatMult ahead of this rank.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/b200_mpiaij.h"
+#include "b200_common.h"
+
+using namespace b200;
+
+namespace {
+
+constexpr int    WINDOW_HDR_BYTES = 1024;
+constexpr int    MAX_RANKS        = 120;
+constexpr int    ERR_WORD         = 126;
+constexpr int    PUSH_CHUNK       = 2048;  // elements per CTA of the push kernel
+
+struct PushBlock {  // one CTA of the push kernel
+  int32_t peer_slot, start, count, pad;
+};
+struct PushPeer {   // one destination
+  double             *dst[2];   // peer lvec buffers at this rank's offset
+  unsigned long long *flag;     // &peer_window.flags[my rank]
+  int32_t             nblocks, pad;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// VecScatterBegin: gather x[send_idx] and store it into each peer's lvec (peer memory), then the
+// last CTA of each peer releases flag = seq.
+__global__ void __launch_bounds__(256)
+    k_halo_push(const PushBlock *__restrict__ blocks, const PushPeer *__restrict__ peers,
+                const int *__restrict__ send_idx, const double *__restrict__ x, unsigned *done,
+                unsigned long long seq)
+{
+  const PushBlock b   = blocks[blockIdx.x];
+  const PushPeer  p   = peers[b.peer_slot];
+  double         *dst = p.dst[seq & 1];
+  for (int t = threadIdx.x; t < b.count; t += blockDim.x) {
+    const int e = b.start + t;
+    dst[e]      = __ldg(x + send_idx[e]);   // send_idx is per peer: e indexes the peer's run
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done + b.peer_slot, 1u);
+    if (prev == (unsigned)p.nblocks - 1) {
+      done[b.peer_slot] = 0;
+      __threadfence_system();
+      st_release_sys(p.flag, seq);
+    }
+  }
+}
+
+// pack only (transport owned by the caller)
+__global__ void k_halo_pack(int count, const int *__restrict__ send_idx, const double *__restrict__ x, double *buf)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) buf[t] = __ldg(x + send_idx[t]);
+}
+
+// VecScatterEnd + MatMultAdd_SeqAIJ(B, lvec, y, y), compressed-row: thread per non-empty row of B.
+// WAIT: thread 0 of every CTA acquires the source flags (>= seq) before the CTA reads lvec.
+template <int MODE, bool WAIT>
+__global__ void __launch_bounds__(128)
+    k_offdiag(int nrows, const int *__restrict__ cpi, const int *__restrict__ ridx,
+              const int *__restrict__ bj, const double *__restrict__ ba, const double *lvec,
+              double *y, const unsigned long long *flags, const int *__restrict__ srcs, int nsrc,
+              unsigned long long seq, unsigned long long *err, unsigned long long timeout_ns)
+{
+  if (WAIT) {
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      for (int s = 0; s < nsrc; ++s) {
+        const unsigned long long *f = flags + srcs[s];
+        while (ld_acquire_sys(f) < seq) {
+          if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(err, 1ull); break; }
+          __nanosleep(64);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows) return;
+  const int lo = cpi[t], hi = cpi[t + 1], i = ridx[t];
+  double    sum = y[i];
+  for (int k = lo; k < hi; ++k) {
+    const double xv = __ldcg(lvec + bj[k]);  // written by a peer GPU: read through L2, not L1
+    sum = (MODE == B200_MODE_EXACT) ? __dadd_rn(sum, __dmul_rn(ba[k], xv)) : __fma_rn(ba[k], xv, sum);
+  }
+  y[i] = sum;
+}
+
+}  // namespace
+
+struct b200_mpiaij_s {
+  int32_t size = 1, rank = 0, nloc = 0, rstart = 0, rend = 0;
+  std::vector<int32_t> base;
+  // host blocks
+  std::vector<int32_t> Ai, Aj, Bi, Bj, garray, recv_off, cpi, ridx, srcs;
+  std::vector<double>  Aa, Ba;
+  // send side
+  struct Send { int32_t peer, count, peer_offset, peer_ngpad; std::vector<int32_t> idx; void *peer_window = nullptr; bool opened = false; };
+  std::vector<Send> sends;  // one per peer that needs something from this rank
+  // device
+  bool      uploaded = false, push_ready = false;
+  b200_csr_t A = nullptr, B = nullptr;
+  int       *d_cpi = nullptr, *d_ridx = nullptr, *d_bj = nullptr, *d_srcs = nullptr, *d_send_idx = nullptr;
+  double    *d_ba = nullptr;
+  unsigned char *d_window = nullptr;
+  size_t     window_bytes = 0;
+  int32_t    ngpad = 0;
+  PushBlock *d_blocks = nullptr;
+  PushPeer  *d_peers = nullptr;
+  unsigned  *d_done = nullptr;
+  int        npush_blocks = 0;
+  std::vector<int32_t> send_start;  // start of each peer's run in d_send_idx
+  unsigned long long seq = 0;
+  cudaStream_t side = nullptr, hstream = nullptr;
+  double *d_hx = nullptr, *d_hy = nullptr;
+  cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
+  unsigned long long timeout_ns = 2000ull * 1000000ull;
+};
+
+static int32_t pad16(int32_t n) { return (n + 15) & ~15; }
+
+extern "C" int b200_mpiaij_create(b200_mpiaij_t *out, int32_t size, int32_t rank,
+                                  const int32_t *base, const int32_t *h_ai,
+                                  const int32_t *h_aj, const double *h_aa)
+{
+  if (!out || size < 1 || size > MAX_RANKS || rank < 0 || rank >= size || !base || !h_ai)
+    return set_error(B200_ERR_ARG, "b200_mpiaij_create: bad argument (size must be 1..%d)", MAX_RANKS);
+  b200_mpiaij_s *M = new (std::nothrow) b200_mpiaij_s;
+  if (!M) return set_error(B200_ERR_MEM, "out of host memory");
+  M->size = size; M->rank = rank;
+  M->base.assign(base, base + size + 1);
+  M->rstart = base[rank]; M->rend = base[rank + 1];
+  M->nloc = M->rend - M->rstart;
+  const int nloc = M->nloc, nz = h_ai[nloc];
+  if (nz && (!h_aj || !h_aa)) { delete M; return set_error(B200_ERR_ARG, "null aj/aa"); }
+  // --- MatSetValues_MPIAIJ split [P376]: owned columns -> A (local ids), others -> B ----------
+  M->Ai.assign(nloc + 1, 0); M->Bi.assign(nloc + 1, 0);
+  M->Aj.reserve(nz); M->Aa.reserve(nz);
+  for (int i = 0; i < nloc; ++i) {
+    for (int k = h_ai[i]; k < h_ai[i + 1]; ++k) {
+      const int c = h_aj[k];
+      if (c < 0 || c >= base[size]) { delete M; return set_error(B200_ERR_ARG, "column %d out of range", c); }
+      if (c >= M->rstart && c < M->rend) { M->Aj.push_back(c - M->rstart); M->Aa.push_back(h_aa[k]); }
+      else { M->Bj.push_back(c); M->Ba.push_back(h_aa[k]); }
+    }
+    M->Ai[i + 1] = (int32_t)M->Aj.size();
+    M->Bi[i + 1] = (int32_t)M->Bj.size();
+  }
+  // --- MatSetUpMultiply_MPIAIJ [P376]: garray = sorted unique ghost ids; compact B's columns ---
+  M->garray = M->Bj;
+  std::sort(M->garray.begin(), M->garray.end());
+  M->garray.erase(std::unique(M->garray.begin(), M->garray.end()), M->garray.end());
+  for (auto &c : M->Bj) c = (int32_t)(std::lower_bound(M->garray.begin(), M->garray.end(), c) - M->garray.begin());
+  // --- receive side of Mvctx: contiguous run of garray per owner ------------------------------
+  M->recv_off.assign(size + 1, 0);
+  {
+    size_t k = 0;
+    for (int q = 0; q < size; ++q) {
+      M->recv_off[q] = (int32_t)k;
+      while (k < M->garray.size() && M->garray[k] < base[q + 1]) ++k;
+    }
+    M->recv_off[size] = (int32_t)k;
+  }
+  for (int q = 0; q < size; ++q)
+    if (q != rank && M->recv_off[q + 1] > M->recv_off[q]) M->srcs.push_back(q);
+  // --- compressed-row index of B (only the rows that touch a ghost) ---------------------------
+  M->cpi.push_back(0);
+  for (int i = 0; i < nloc; ++i)
+    if (M->Bi[i + 1] > M->Bi[i]) { M->cpi.push_back(M->Bi[i + 1]); M->ridx.push_back(i); }
+  M->ngpad = pad16((int32_t)M->garray.size());
+  *out = M;
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_destroy(b200_mpiaij_t M)
+{
+  if (!M) return B200_OK;
+  for (auto &s : M->sends) if (s.opened && s.peer_window) cudaIpcCloseMemHandle(s.peer_window);
+  if (M->A) b200_csr_destroy(M->A);
+  if (M->B) b200_csr_destroy(M->B);
+  cudaFree(M->d_cpi); cudaFree(M->d_ridx); cudaFree(M->d_bj); cudaFree(M->d_ba); cudaFree(M->d_srcs);
+  cudaFree(M->d_send_idx); cudaFree(M->d_window); cudaFree(M->d_blocks); cudaFree(M->d_peers); cudaFree(M->d_done);
+  if (M->side) cudaStreamDestroy(M->side);
+  if (M->hstream) cudaStreamDestroy(M->hstream);
+  cudaFree(M->d_hx); cudaFree(M->d_hy);
+  if (M->ev_fork) cudaEventDestroy(M->ev_fork);
+  if (M->ev_join) cudaEventDestroy(M->ev_join);
+  delete M;
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_get_sizes(b200_mpiaij_t M, int32_t *s)
+{
+  if (!M || !s) return set_error(B200_ERR_ARG, "null argument");
+  s[0] = M->nloc; s[1] = (int32_t)M->Aj.size(); s[2] = (int32_t)M->Bj.size();
+  s[3] = (int32_t)M->garray.size(); s[4] = (int32_t)M->ridx.size(); s[5] = (int32_t)M->srcs.size();
+  return B200_OK;
+}
+extern "C" int b200_mpiaij_get_garray(b200_mpiaij_t M, int32_t *g)
+{
+  if (!M || (!g && !M->garray.empty())) return set_error(B200_ERR_ARG, "null argument");
+  if (!M->garray.empty()) memcpy(g, M->garray.data(), M->garray.size() * sizeof(int32_t));
+  return B200_OK;
+}
+extern "C" int b200_mpiaij_get_recv_offsets(b200_mpiaij_t M, int32_t *off)
+{
+  if (!M || !off) return set_error(B200_ERR_ARG, "null argument");
+  memcpy(off, M->recv_off.data(), M->recv_off.size() * sizeof(int32_t));
+  return B200_OK;
+}
+extern "C" int b200_mpiaij_copy_block(b200_mpiaij_t M, int which, int32_t *ai, int32_t *aj, double *aa)
+{
+  if (!M || which < 0 || which > 1) return set_error(B200_ERR_ARG, "bad argument");
+  const auto &I = which ? M->Bi : M->Ai;
+  const auto &J = which ? M->Bj : M->Aj;
+  const auto &V = which ? M->Ba : M->Aa;
+  if (ai) memcpy(ai, I.data(), I.size() * sizeof(int32_t));
+  if (aj && !J.empty()) memcpy(aj, J.data(), J.size() * sizeof(int32_t));
+  if (aa && !V.empty()) memcpy(aa, V.data(), V.size() * sizeof(double));
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_set_peer_garray(b200_mpiaij_t M, int32_t peer, const int32_t *pg, int32_t png)
+{
+  if (!M || peer < 0 || peer >= M->size || png < 0 || (png && !pg)) return set_error(B200_ERR_ARG, "bad argument");
+  if (peer == M->rank) return B200_OK;
+  if (M->push_ready) return set_error(B200_ERR_STATE, "send lists are frozen after the first MatMult");
+  const int32_t *lo = std::lower_bound(pg, pg + png, M->rstart);
+  const int32_t *hi = std::lower_bound(pg, pg + png, M->rend);
+  for (auto it = M->sends.begin(); it != M->sends.end(); ++it)
+    if (it->peer == peer) { M->sends.erase(it); break; }
+  if (hi == lo) return B200_OK;
+  b200_mpiaij_s::Send s;
+  s.peer = peer; s.count = (int32_t)(hi - lo); s.peer_offset = (int32_t)(lo - pg); s.peer_ngpad = pad16(png);
+  s.idx.resize(s.count);
+  for (int32_t t = 0; t < s.count; ++t) s.idx[t] = lo[t] - M->rstart;
+  M->sends.push_back(std::move(s));
+  std::sort(M->sends.begin(), M->sends.end(), [](const b200_mpiaij_s::Send &a, const b200_mpiaij_s::Send &b) { return a.peer < b.peer; });
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_get_send_list(b200_mpiaij_t M, int32_t peer, int32_t *count, int32_t *idx, int32_t *peer_offset)
+{
+  if (!M || !count) return set_error(B200_ERR_ARG, "null argument");
+  *count = 0;
+  for (auto &s : M->sends)
+    if (s.peer == peer) {
+      *count = s.count;
+      if (peer_offset) *peer_offset = s.peer_offset;
+      if (idx) memcpy(idx, s.idx.data(), s.idx.size() * sizeof(int32_t));
+    }
+  return B200_OK;
+}
+
+template <typename T>
+static int up(T **d, const std::vector<T> &h)
+{
+  B200_CUDA_TRY(cudaMalloc((void **)d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  if (!h.empty()) B200_CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
+{
+  if (!M) return set_error(B200_ERR_ARG, "null handle");
+  if (M->uploaded) return B200_OK;
+  B200_TRY(ensure_device());
+  B200_TRY(b200_csr_create(&M->A, M->nloc, M->nloc, M->Ai.data(), M->Aj.data(), M->Aa.data()));
+  B200_TRY(b200_csr_create(&M->B, M->nloc, (int32_t)M->garray.size(), M->Bi.data(), M->Bj.data(), M->Ba.data()));
+  B200_TRY(up(&M->d_cpi, M->cpi));
+  B200_TRY(up(&M->d_ridx, M->ridx));
+  B200_TRY(up(&M->d_bj, M->Bj));
+  B200_TRY(up(&M->d_ba, M->Ba));
+  B200_TRY(up(&M->d_srcs, M->srcs));
+  M->window_bytes = WINDOW_HDR_BYTES + (size_t)2 * M->ngpad * sizeof(double) + 256;
+  B200_CUDA_TRY(cudaMalloc((void **)&M->d_window, M->window_bytes));
+  B200_CUDA_TRY(cudaMemset(M->d_window, 0, M->window_bytes));
+  B200_CUDA_TRY(cudaStreamCreateWithFlags(&M->side, cudaStreamNonBlocking));
+  B200_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_fork, cudaEventDisableTiming));
+  B200_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_join, cudaEventDisableTiming));
+  M->timeout_ns = (unsigned long long)env_int("B200_MPIAIJ_TIMEOUT_MS", 2000) * 1000000ull;
+  B200_CUDA_TRY(cudaDeviceSynchronize());
+  M->uploaded = true;
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_get_blocks(b200_mpiaij_t M, b200_csr_t *A, b200_csr_t *B)
+{
+  if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  if (A) *A = M->A;
+  if (B) *B = M->B;
+  return B200_OK;
+}
+extern "C" int b200_mpiaij_window_ipc_handle(b200_mpiaij_t M, void *handle64)
+{
+  if (!M || !M->uploaded || !handle64) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  cudaIpcMemHandle_t h;
+  B200_CUDA_TRY(cudaIpcGetMemHandle(&h, M->d_window));
+  memcpy(handle64, &h, 64);
+  return B200_OK;
+}
+extern "C" int b200_mpiaij_window_ptr(b200_mpiaij_t M, void **d)
+{
+  if (!M || !M->uploaded || !d) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  *d = M->d_window;
+  return B200_OK;
+}
+extern "C" int b200_mpiaij_set_peer_window(b200_mpiaij_t M, int32_t peer, void *d_window)
+{
+  if (!M) return set_error(B200_ERR_ARG, "null handle");
+  for (auto &s : M->sends) if (s.peer == peer) { s.peer_window = d_window; s.opened = false; }
+  M->push_ready = false;
+  return B200_OK;
+}
+extern "C" int b200_mpiaij_open_peer_window(b200_mpiaij_t M, int32_t peer, const void *handle64)
+{
+  if (!M || !handle64) return set_error(B200_ERR_ARG, "null argument");
+  for (auto &s : M->sends)
+    if (s.peer == peer) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handle64, 64);
+      void *p = nullptr;
+      B200_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      s.peer_window = p;
+      s.opened = true;
+    }
+  M->push_ready = false;
+  return B200_OK;
+}
+
+// freeze the send side: flat index array, CTA table, per-peer destinations
+static int prepare_push(b200_mpiaij_s *M)
+{
+  if (M->push_ready) return B200_OK;
+  cudaFree(M->d_send_idx); cudaFree(M->d_blocks); cudaFree(M->d_peers); cudaFree(M->d_done);
+  M->d_send_idx = nullptr; M->d_blocks = nullptr; M->d_peers = nullptr; M->d_done = nullptr;
+  std::vector<int32_t>   flat;
+  std::vector<PushBlock> blocks;
+  std::vector<PushPeer>  peers;
+  M->send_start.clear();
+  int slot = 0;
+  for (auto &s : M->sends) {
+    if (!s.peer_window) return set_error(B200_ERR_STATE, "peer %d needs data but its window is not mapped", s.peer);
+    unsigned char *w = (unsigned char *)s.peer_window;
+    PushPeer p;
+    // dst is biased by -start so that the kernel can index with the flat element number
+    const int32_t start = (int32_t)flat.size();
+    p.dst[0] = (double *)(w + WINDOW_HDR_BYTES) + s.peer_offset - start;
+    p.dst[1] = (double *)(w + WINDOW_HDR_BYTES) + s.peer_ngpad + s.peer_offset - start;
+    p.flag   = (unsigned long long *)w + M->rank;
+    p.nblocks = (s.count + PUSH_CHUNK - 1) / PUSH_CHUNK;
+    p.pad = 0;
+    for (int b = 0; b < p.nblocks; ++b)
+      blocks.push_back(PushBlock{slot, start + b * PUSH_CHUNK, std::min(PUSH_CHUNK, s.count - b * PUSH_CHUNK), 0});
+    M->send_start.push_back(start);
+    flat.insert(flat.end(), s.idx.begin(), s.idx.end());
+    peers.push_back(p);
+    ++slot;
+  }
+  M->npush_blocks = (int)blocks.size();
+  B200_TRY(up(&M->d_send_idx, flat));
+  B200_TRY(up(&M->d_blocks, blocks));
+  B200_TRY(up(&M->d_peers, peers));
+  B200_CUDA_TRY(cudaMalloc((void **)&M->d_done, sizeof(unsigned) * std::max<size_t>(peers.size(), 1)));
+  B200_CUDA_TRY(cudaMemset(M->d_done, 0, sizeof(unsigned) * std::max<size_t>(peers.size(), 1)));
+  M->push_ready = true;
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_mult_begin(b200_mpiaij_t M, const double *d_x, void *stream)
+{
+  if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  B200_TRY(prepare_push(M));
+  M->seq += 1;
+  if (M->npush_blocks)
+    B200_LAUNCH(k_halo_push, M->npush_blocks, 256, 0, (cudaStream_t)stream, M->d_blocks, M->d_peers,
+                M->d_send_idx, d_x, M->d_done, M->seq);
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_mult_local(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream)
+{
+  if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  return b200_spmv(M->A, d_x, d_y, mode, stream);
+}
+
+static int offdiag(b200_mpiaij_s *M, const double *lvec, double *d_y, int mode, bool wait, cudaStream_t st)
+{
+  const int nrows = (int)M->ridx.size();
+  if (!nrows) return B200_OK;
+  const unsigned long long *flags = (const unsigned long long *)M->d_window;
+  unsigned long long       *err   = (unsigned long long *)M->d_window + ERR_WORD;
+  const int grid = (nrows + 127) / 128, nsrc = (int)M->srcs.size();
+#define OFFDIAG(MODE_, WAIT_)                                                                   \
+  B200_LAUNCH((k_offdiag<MODE_, WAIT_>), grid, 128, 0, st, nrows, M->d_cpi, M->d_ridx, M->d_bj,  \
+              M->d_ba, lvec, d_y, flags, M->d_srcs, nsrc, M->seq, err, M->timeout_ns)
+  if (mode == B200_MODE_EXACT) { if (wait) OFFDIAG(B200_MODE_EXACT, true); else OFFDIAG(B200_MODE_EXACT, false); }
+  else { if (wait) OFFDIAG(B200_MODE_EXACT_FMA, true); else OFFDIAG(B200_MODE_EXACT_FMA, false); }
+#undef OFFDIAG
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_mult_end(b200_mpiaij_t M, double *d_y, int mode, void *stream)
+{
+  if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  const double *lvec = (const double *)(M->d_window + WINDOW_HDR_BYTES) + (size_t)(M->seq & 1) * M->ngpad;
+  return offdiag(M, lvec, d_y, mode, true, (cudaStream_t)stream);
+}
+
+extern "C" int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream)
+{
+  if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_TRY(prepare_push(M));
+  if (M->npush_blocks) {
+    // fork: the push runs beside A x; join so that the caller may overwrite x afterwards
+    B200_CUDA_TRY(cudaEventRecord(M->ev_fork, st));
+    B200_CUDA_TRY(cudaStreamWaitEvent(M->side, M->ev_fork, 0));
+    B200_TRY(b200_mpiaij_mult_begin(M, d_x, M->side));
+    B200_CUDA_TRY(cudaEventRecord(M->ev_join, M->side));
+  } else {
+    M->seq += 1;
+  }
+  B200_TRY(b200_mpiaij_mult_local(M, d_x, d_y, mode, st));
+  B200_TRY(b200_mpiaij_mult_end(M, d_y, mode, st));
+  if (M->npush_blocks) B200_CUDA_TRY(cudaStreamWaitEvent(st, M->ev_join, 0));
+  return B200_OK;
+}
+
+// MatMult_MPIAIJ(Mat,Vec,Vec) with host Vecs: upload this rank's x rows, multiply, download y.
+extern "C" int b200_mpiaij_mult_host(b200_mpiaij_t M, const double *h_x, double *h_y, int mode)
+{
+  if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  if (!M->d_hx) {
+    B200_CUDA_TRY(cudaMalloc((void **)&M->d_hx, std::max<size_t>(M->nloc, 1) * sizeof(double)));
+    B200_CUDA_TRY(cudaMalloc((void **)&M->d_hy, std::max<size_t>(M->nloc, 1) * sizeof(double)));
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&M->hstream, cudaStreamNonBlocking));
+  }
+  B200_CUDA_TRY(cudaMemcpyAsync(M->d_hx, h_x, (size_t)M->nloc * sizeof(double), cudaMemcpyHostToDevice, M->hstream));
+  B200_TRY(b200_mpiaij_mult(M, M->d_hx, M->d_hy, mode, M->hstream));
+  B200_CUDA_TRY(cudaMemcpyAsync(h_y, M->d_hy, (size_t)M->nloc * sizeof(double), cudaMemcpyDeviceToHost, M->hstream));
+  B200_CUDA_TRY(cudaStreamSynchronize(M->hstream));
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_pack(b200_mpiaij_t M, int32_t peer, const double *d_x, double *d_buf, void *stream)
+{
+  if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  // a flat index array is needed; build it without requiring peer windows
+  if (!M->d_send_idx) {
+    std::vector<int32_t> flat;
+    M->send_start.clear();
+    for (auto &s : M->sends) { M->send_start.push_back((int32_t)flat.size()); flat.insert(flat.end(), s.idx.begin(), s.idx.end()); }
+    B200_TRY(up(&M->d_send_idx, flat));
+  }
+  for (size_t k = 0; k < M->sends.size(); ++k)
+    if (M->sends[k].peer == peer) {
+      const int cnt = M->sends[k].count;
+      B200_LAUNCH(k_halo_pack, (cnt + 255) / 256, 256, 0, (cudaStream_t)stream, cnt, M->d_send_idx + M->send_start[k], d_x, d_buf);
+      return B200_OK;
+    }
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_mult_add_ghost(b200_mpiaij_t M, const double *d_lvec, double *d_y, int mode, void *stream)
+{
+  if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  return offdiag(M, d_lvec, d_y, mode, false, (cudaStream_t)stream);
+}
+
+extern "C" int b200_mpiaij_check(b200_mpiaij_t M)
+{
+  if (!M || !M->uploaded) return B200_OK;
+  unsigned long long e = 0;
+  B200_CUDA_TRY(cudaMemcpy(&e, (unsigned long long *)M->d_window + ERR_WORD, sizeof e, cudaMemcpyDeviceToHost));
+  if (e) return set_error(B200_ERR_TIMEOUT, "rank %d: a halo flag was not seen within the spin budget", M->rank);
+  return B200_OK;
+}

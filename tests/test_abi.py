@@ -25,7 +25,7 @@ def declared_symbols():
 
 
 def test_every_declared_symbol_is_exported(pk):
-    libs = {"b200_seqaij.h": pk.lib}
+    libs = {"b200_seqaij.h": pk.lib, "b200_mpiaij.h": pk.lib}
     host = os.path.join(ROOT, "petsc-openacc_b200", "libb200petsc.so")
     if os.path.exists(host):
         libs["b200_petsc_symbols.h"] = C.CDLL(host)

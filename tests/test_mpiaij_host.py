@@ -1,0 +1,112 @@
+"""Host-side integer work of the MatMult_MPIAIJ path (A/B split, garray, scatter lists) against
+the oracle, in-process and across two gloo ranks.  Bit-exact bar."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+
+
+def build_rank(pk, N, size, rank):
+    g = pk.gen_poisson7(N, size, rank)
+    return pk.MpiAij(size, rank, g["base"], g["ai"], g["aj"], g["aa"]), g
+
+
+def oracle_rank(N, size, rank):
+    p = oracle.poisson7(N, size=size, rank=rank)
+    (Ai, Aj, Aa), (Bi, Bj, Ba) = oracle.mpiaij_split(p["ai"], p["aj"], p["aa"], p["rstart"], p["rend"])
+    Bjc, garray = oracle.mpiaij_setup_multiply(Bj)
+    return dict(A=(Ai, Aj, Aa), B=(Bi, Bjc, Ba), garray=garray, p=p)
+
+
+@pytest.mark.parametrize("N,size", [(6, 1), (10, 2), (12, 4), (12, 8), (13, 8), (10, 3), (9, 6)])
+def test_split_garray_and_scatter_lists(pk, N, size):
+    base = oracle.dmda_bases(N, N, N, size)
+    ranks = [build_rank(pk, N, size, r)[0] for r in range(size)]
+    refs = [oracle_rank(N, size, r) for r in range(size)]
+    for r, (M, o) in enumerate(zip(ranks, refs)):
+        for which, key in ((0, "A"), (1, "B")):
+            ai, aj, aa = M.block(which)
+            assert np.array_equal(ai, o[key][0]) and np.array_equal(aj, o[key][1]) and np.array_equal(aa, o[key][2])
+        assert np.array_equal(M.garray(), o["garray"])
+        assert np.array_equal(M.recv_offsets(), oracle.scatter_recv_offsets(base, o["garray"]))
+        assert M.brows == int((np.diff(o["B"][0]) > 0).sum())
+    # scatter lists: what rank r sends to q is q's garray run inside r's rows, in garray order
+    for r, M in enumerate(ranks):
+        for q in range(size):
+            M.set_peer_garray(q, refs[q]["garray"])
+        for q in range(size):
+            idx, off = M.send_list(q)
+            if q == r:
+                assert len(idx) == 0
+                continue
+            roff = oracle.scatter_recv_offsets(base, refs[q]["garray"])
+            seg = refs[q]["garray"][roff[r]:roff[r + 1]]
+            assert np.array_equal(idx, seg - base[r])
+            if len(seg):
+                assert off == roff[r]
+    for M in ranks:
+        M.destroy()
+
+
+def test_survey_halo_sizes_scaled(pk):
+    """2x2x2 grid -> three face neighbours; per-rank halo = 3 faces."""
+    N, size = 20, 8
+    M, _ = build_rank(pk, N, size, 0)
+    h = N // 2
+    assert (M.nloc, M.nghost, M.bnnz, M.nsrc) == (h ** 3, 3 * h * h, 3 * h * h, 3)
+    assert M.annz == 7 * h ** 3 - 6 * h ** 2
+    assert M.brows == 3 * h * h - 3 * h + 1
+    M.destroy()
+    M2, _ = build_rank(pk, N, 2, 0)
+    assert (M2.nghost, M2.nsrc) == (N * N, 1)
+    M2.destroy()
+
+
+def _gloo_worker(rank, world, N, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import petsc_openacc_b200 as pk
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        M, g = build_rank(pk, N, world, rank)
+        garrays = [None] * world
+        dist.all_gather_object(garrays, M.garray())
+        for peer in range(world):
+            M.set_peer_garray(peer, garrays[peer])
+        out = {p: M.send_list(p) for p in range(world)}
+        q.put((rank, M.garray(), out, M.recv_offsets()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_exchange_of_scatter_lists(pk):
+    import torch.multiprocessing as mp
+    N, world = 10, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, N, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, garray, sends, roff = q.get(timeout=180)
+        res[r] = (garray, sends, roff)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    base = oracle.dmda_bases(N, N, N, world)
+    refs = [oracle_rank(N, world, r) for r in range(world)]
+    for r in range(world):
+        garray, sends, roff = res[r]
+        assert np.array_equal(garray, refs[r]["garray"])
+        peer = 1 - r
+        idx, off = sends[peer]
+        proff = oracle.scatter_recv_offsets(base, refs[peer]["garray"])
+        assert np.array_equal(idx, refs[peer]["garray"][proff[r]:proff[r + 1]] - base[r])
+        assert off == proff[r] and len(idx) == N * N
