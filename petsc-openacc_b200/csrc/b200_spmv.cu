@@ -341,19 +341,22 @@ static int stream_set_attr(size_t smem)
   return B200_OK;
 }
 
-static int stream_set_all_attrs(int threads, size_t smem)
+// The opt-in limit is a per-function, process-wide attribute: raise it once to the architectural
+// maximum so that matrices with different stage sizes can coexist.
+static int stream_set_all_attrs(int /*threads*/, size_t /*smem*/)
 {
-  if (threads == 256) {
-    B200_TRY((stream_set_attr<B200_MODE_EXACT, false, 256>(smem)));
-    B200_TRY((stream_set_attr<B200_MODE_EXACT, true, 256>(smem)));
-    B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, false, 256>(smem)));
-    B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, true, 256>(smem)));
-  } else {
-    B200_TRY((stream_set_attr<B200_MODE_EXACT, false, 128>(smem)));
-    B200_TRY((stream_set_attr<B200_MODE_EXACT, true, 128>(smem)));
-    B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, false, 128>(smem)));
-    B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, true, 128>(smem)));
-  }
+  static bool done = false;
+  if (done) return B200_OK;
+  const size_t maxsmem = 227 * 1024;
+  B200_TRY((stream_set_attr<B200_MODE_EXACT, false, 256>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT, true, 256>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, false, 256>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, true, 256>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT, false, 128>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT, true, 128>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, false, 128>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, true, 128>(maxsmem)));
+  done = true;
   return B200_OK;
 }
 
