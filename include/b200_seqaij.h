@@ -126,6 +126,8 @@ int b200_spmv_transpose_add(b200_csr_t A, const double *d_x, const double *d_z, 
 int b200_spmv_host(b200_csr_t A, const double *h_x, double *h_y, int mode);
 int b200_spmv_add_host(b200_csr_t A, const double *h_x, const double *h_y, double *h_z, int mode);
 int b200_spmv_transpose_host(b200_csr_t A, const double *h_x, double *h_y, int mode);
+int b200_spmv_transpose_add_host(b200_csr_t A, const double *h_x, const double *h_z, double *h_y,
+                                int mode);
 /* Pinned host allocation for Vec arrays (page-locked memory makes the copies above async).   */
 int b200_host_alloc(void **p, size_t bytes);
 int b200_host_free(void *p);

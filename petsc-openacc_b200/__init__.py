@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "b200_csr_destroy", "b200_csr_get_info", "b200_csr_set_kernel", "b200_csr_build_transpose",
     "b200_csr_device_arrays", "b200_spmv", "b200_spmv_add", "b200_spmv_transpose",
     "b200_spmv_transpose_add", "b200_spmv_host", "b200_spmv_add_host",
-    "b200_spmv_transpose_host", "b200_host_alloc", "b200_host_free", "b200_host_register",
+    "b200_spmv_transpose_host", "b200_spmv_transpose_add_host", "b200_host_alloc", "b200_host_free", "b200_host_register",
     "b200_host_unregister", "b200_vec_set", "b200_vec_copy", "b200_vec_axpy", "b200_vec_aypx",
     "b200_vec_pointwise_mult", "b200_vec_dot", "b200_vec_norm2", "b200_vec_norm_inf",
     "b200_vec_sum", "b200_cg_jacobi", "b200_gen_vector",

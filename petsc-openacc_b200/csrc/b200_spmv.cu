@@ -839,6 +839,20 @@ extern "C" int b200_spmv_transpose_host(b200_csr_t A, const double *h_x, double 
   return B200_OK;
 }
 
+extern "C" int b200_spmv_transpose_add_host(b200_csr_t A, const double *h_x, const double *h_z, double *h_y, int mode)
+{
+  if (!A || (!h_x && A->m) || ((!h_y || !h_z) && A->n)) return set_error(B200_ERR_ARG, "b200_spmv_transpose_add_host: null argument");
+  B200_TRY(check_mode(mode));
+  B200_TRY(host_scratch(A, A->m, A->n));
+  cudaStream_t s = A->hs[0];
+  B200_CUDA_TRY(cudaMemcpyAsync(A->d_hx, h_x, (size_t)A->m * sizeof(double), cudaMemcpyHostToDevice, s));
+  B200_CUDA_TRY(cudaMemcpyAsync(A->d_hy, h_z, (size_t)A->n * sizeof(double), cudaMemcpyHostToDevice, s));
+  B200_TRY(transpose_common(A, A->d_hx, A->d_hy, A->d_hy, mode, s));
+  B200_CUDA_TRY(cudaMemcpyAsync(h_y, A->d_hy, (size_t)A->n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  B200_CUDA_TRY(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
 extern "C" int b200_host_alloc(void **p, size_t bytes)
 {
   if (!p) return set_error(B200_ERR_ARG, "null pointer");
