@@ -65,11 +65,15 @@ int b200_mpiaij_set_peer_window(b200_mpiaij_t M, int32_t peer, void *d_window); 
 
 /* y = A x_local + B x_ghost.  begin = VecScatterBegin (pack + push + release flags),
  * local = A x, end = VecScatterEnd + MatMultAdd (acquire flags, y += B lvec).
- * b200_mpiaij_mult runs the three: push on an internal side stream, A then B on `stream`.     */
+ * b200_mpiaij_mult runs the three in ONE kernel launch when the diagonal block uses the stream
+ * kernel (push CTAs first in the grid, B rows folded into the tile loop); otherwise the push goes
+ * to an internal side stream and A, B run on `stream`.                                          */
 int b200_mpiaij_mult_begin(b200_mpiaij_t M, const double *d_x, void *stream);
 int b200_mpiaij_mult_local(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream);
 int b200_mpiaij_mult_end(b200_mpiaij_t M, double *d_y, int mode, void *stream);
 int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream);
+/* A x + B lvec after a separate b200_mpiaij_mult_begin (one fused launch when possible).        */
+int b200_mpiaij_mult_finish(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream);
 /* The same with HOST vectors (PETSc 3.7.6 Vecs): this rank's x rows up, y rows down, synchronous. */
 int b200_mpiaij_mult_host(b200_mpiaij_t M, const double *h_x, double *h_y, int mode);
 /* Variant for a transport owned by the caller (NCCL send/recv through torch.distributed):

@@ -287,7 +287,7 @@ MPIAIJ_SYMBOLS = [
     "b200_mpiaij_window_ipc_handle", "b200_mpiaij_window_ptr", "b200_mpiaij_open_peer_window",
     "b200_mpiaij_set_peer_window", "b200_mpiaij_mult_begin", "b200_mpiaij_mult_local",
     "b200_mpiaij_mult_end", "b200_mpiaij_mult", "b200_mpiaij_pack", "b200_mpiaij_mult_add_ghost",
-    "b200_mpiaij_check", "b200_mpiaij_mult_host",
+    "b200_mpiaij_check", "b200_mpiaij_mult_host", "b200_mpiaij_mult_finish",
 ]
 ABI_SYMBOLS += MPIAIJ_SYMBOLS
 
@@ -373,6 +373,9 @@ class MpiAij:
 
     def mult(self, x, y, mode=MODE_FAST, stream=None):
         check(lib.b200_mpiaij_mult(self._h, _dptr(x), _dptr(y), C.c_int(mode), _stream(stream)))
+
+    def mult_finish(self, x, y, mode=MODE_FAST, stream=None):
+        check(lib.b200_mpiaij_mult_finish(self._h, _dptr(x), _dptr(y), C.c_int(mode), _stream(stream)))
 
     def mult_host(self, hx, hy, mode=MODE_FAST):
         check(lib.b200_mpiaij_mult_host(self._h, _np_ptr(hx), _np_ptr(hy), C.c_int(mode)))

@@ -41,6 +41,94 @@ int  env_int(const char *name, int dflt);
     B200_CUDA_TRY(cudaGetLastError());                                                         \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Halo pieces shared by b200_halo.cu (owner) and the fused stream kernel in b200_spmv.cu.
+// ---------------------------------------------------------------------------------------------
+struct PushBlock {  // one CTA of the push role
+  int32_t peer_slot, start, count, pad;
+};
+struct PushPeer {   // one destination rank
+  double             *dst[2];  // peer lvec buffers (biased so that the flat element number indexes)
+  unsigned long long *flag;    // &peer_window.flags[my rank]
+  int32_t             nblocks, pad;
+};
+struct HaloArgs {
+  // send side (VecScatterBegin)
+  const PushBlock *blocks;
+  const PushPeer  *peers;
+  const int       *send_idx;
+  unsigned        *done;
+  int              npush;
+  // receive side (VecScatterEnd + MatMultAdd of the off-diagonal block, compressed row)
+  const int2      *btiles;     // per stream tile: [first, last) position in the compressed-row index
+  const int       *cpi, *ridx, *bj;
+  const double    *ba;
+  const double    *lvec;
+  const unsigned long long *flags;
+  const int       *srcs;
+  int              nsrc;
+  unsigned long long seq;
+  unsigned long long *err;
+  unsigned long long  timeout_ns;
+};
+// internal (not part of the C ABI): the stream plan of a matrix and the fused launch
+int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles);   // 0 tiles = not applicable
+int launch_stream_halo(b200_csr_t A, const double *x, double *y, int mode, const HaloArgs &h,
+                       cudaStream_t st);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// the push role: gather x[send_idx] into the peer's lvec over NVLink; the last CTA of a peer
+// releases that peer's flag
+__device__ __forceinline__ void halo_push_block(const HaloArgs &h, const double *__restrict__ x, int block)
+{
+  const PushBlock b   = h.blocks[block];
+  const PushPeer  p   = h.peers[b.peer_slot];
+  double         *dst = p.dst[h.seq & 1];
+  for (int t = threadIdx.x; t < b.count; t += blockDim.x) {
+    const int e = b.start + t;
+    dst[e]      = __ldg(x + h.send_idx[e]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(h.done + b.peer_slot, 1u);
+    if (prev == (unsigned)p.nblocks - 1) {
+      h.done[b.peer_slot] = 0;
+      __threadfence_system();
+      st_release_sys(p.flag, h.seq);
+    }
+  }
+}
+// acquire every source rank's flag (>= seq), bounded by the spin budget
+__device__ __forceinline__ void halo_wait_flags(const HaloArgs &h)
+{
+  const unsigned long long t0 = globaltimer_ns();
+  for (int s = 0; s < h.nsrc; ++s) {
+    const unsigned long long *f = h.flags + h.srcs[s];
+    while (ld_acquire_sys(f) < h.seq) {
+      if (globaltimer_ns() - t0 > h.timeout_ns) { atomicExch(h.err, 1ull); break; }
+      __nanosleep(64);
+    }
+  }
+}
+#endif
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk-copy (TMA engine, 1-D) helpers.  SASS: SYNCS.* and UBLKCP.

@@ -30,32 +30,6 @@ constexpr int    MAX_RANKS        = 120;
 constexpr int    ERR_WORD         = 126;
 constexpr int    PUSH_CHUNK       = 2048;  // elements per CTA of the push kernel
 
-struct PushBlock {  // one CTA of the push kernel
-  int32_t peer_slot, start, count, pad;
-};
-struct PushPeer {   // one destination
-  double             *dst[2];   // peer lvec buffers at this rank's offset
-  unsigned long long *flag;     // &peer_window.flags[my rank]
-  int32_t             nblocks, pad;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns()
-{
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
 // VecScatterBegin: gather x[send_idx] and store it into each peer's lvec (peer memory), then the
 // last CTA of each peer releases flag = seq.
 __global__ void __launch_bounds__(256)
@@ -63,23 +37,9 @@ __global__ void __launch_bounds__(256)
                 const int *__restrict__ send_idx, const double *__restrict__ x, unsigned *done,
                 unsigned long long seq)
 {
-  const PushBlock b   = blocks[blockIdx.x];
-  const PushPeer  p   = peers[b.peer_slot];
-  double         *dst = p.dst[seq & 1];
-  for (int t = threadIdx.x; t < b.count; t += blockDim.x) {
-    const int e = b.start + t;
-    dst[e]      = __ldg(x + send_idx[e]);   // send_idx is per peer: e indexes the peer's run
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(done + b.peer_slot, 1u);
-    if (prev == (unsigned)p.nblocks - 1) {
-      done[b.peer_slot] = 0;
-      __threadfence_system();
-      st_release_sys(p.flag, seq);
-    }
-  }
+  HaloArgs h{};
+  h.blocks = blocks; h.peers = peers; h.send_idx = send_idx; h.done = done; h.seq = seq;
+  halo_push_block(h, x, blockIdx.x);
 }
 
 // pack only (transport owned by the caller)
@@ -100,14 +60,9 @@ __global__ void __launch_bounds__(128)
 {
   if (WAIT) {
     if (threadIdx.x == 0) {
-      const unsigned long long t0 = globaltimer_ns();
-      for (int s = 0; s < nsrc; ++s) {
-        const unsigned long long *f = flags + srcs[s];
-        while (ld_acquire_sys(f) < seq) {
-          if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(err, 1ull); break; }
-          __nanosleep(64);
-        }
-      }
+      HaloArgs h{};
+      h.flags = flags; h.srcs = srcs; h.nsrc = nsrc; h.seq = seq; h.err = err; h.timeout_ns = timeout_ns;
+      halo_wait_flags(h);
     }
     __syncthreads();
   }
@@ -151,6 +106,8 @@ struct b200_mpiaij_s {
   double *d_hx = nullptr, *d_hy = nullptr;
   cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
   unsigned long long timeout_ns = 2000ull * 1000000ull;
+  int2 *d_btiles = nullptr;   // fused launch: compressed-row range of B per stream tile of A
+  bool  fused_ok = false;
 };
 
 static int32_t pad16(int32_t n) { return (n + 15) & ~15; }
@@ -215,6 +172,7 @@ extern "C" int b200_mpiaij_destroy(b200_mpiaij_t M)
   if (M->A) b200_csr_destroy(M->A);
   if (M->B) b200_csr_destroy(M->B);
   cudaFree(M->d_cpi); cudaFree(M->d_ridx); cudaFree(M->d_bj); cudaFree(M->d_ba); cudaFree(M->d_srcs);
+  cudaFree(M->d_btiles);
   cudaFree(M->d_send_idx); cudaFree(M->d_window); cudaFree(M->d_blocks); cudaFree(M->d_peers); cudaFree(M->d_done);
   if (M->side) cudaStreamDestroy(M->side);
   if (M->hstream) cudaStreamDestroy(M->hstream);
@@ -315,6 +273,26 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
   B200_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_fork, cudaEventDisableTiming));
   B200_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_join, cudaEventDisableTiming));
   M->timeout_ns = (unsigned long long)env_int("B200_MPIAIJ_TIMEOUT_MS", 2000) * 1000000ull;
+  // fused launch: for every stream tile of A, the run of B's compressed rows inside it
+  {
+    int4 *d_tiles = nullptr;
+    int   ntiles  = 0;
+    B200_TRY(stream_plan_tiles(M->A, &d_tiles, &ntiles));
+    if (ntiles && env_int("B200_MPIAIJ_FUSED", 1)) {
+      std::vector<int4> tiles((size_t)ntiles);
+      B200_CUDA_TRY(cudaMemcpy(tiles.data(), d_tiles, sizeof(int4) * (size_t)ntiles, cudaMemcpyDeviceToHost));
+      std::vector<int2> bt((size_t)ntiles);
+      size_t c = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        while (c < M->ridx.size() && M->ridx[c] < tiles[t].x) ++c;
+        bt[t].x = (int)c;
+        while (c < M->ridx.size() && M->ridx[c] < tiles[t].y) ++c;
+        bt[t].y = (int)c;
+      }
+      B200_TRY(up(&M->d_btiles, bt));
+      M->fused_ok = true;
+    }
+  }
   B200_CUDA_TRY(cudaDeviceSynchronize());
   M->uploaded = true;
   return B200_OK;
@@ -444,11 +422,38 @@ extern "C" int b200_mpiaij_mult_end(b200_mpiaij_t M, double *d_y, int mode, void
   return offdiag(M, lvec, d_y, mode, true, (cudaStream_t)stream);
 }
 
+static HaloArgs fused_args(b200_mpiaij_s *M, bool with_push)
+{
+  HaloArgs h{};
+  h.blocks = M->d_blocks; h.peers = M->d_peers; h.send_idx = M->d_send_idx; h.done = M->d_done;
+  h.npush = with_push ? M->npush_blocks : 0;
+  h.btiles = M->d_btiles; h.cpi = M->d_cpi; h.ridx = M->d_ridx; h.bj = M->d_bj; h.ba = M->d_ba;
+  h.lvec = (const double *)(M->d_window + WINDOW_HDR_BYTES) + (size_t)(M->seq & 1) * M->ngpad;
+  h.flags = (const unsigned long long *)M->d_window; h.srcs = M->d_srcs; h.nsrc = (int)M->srcs.size();
+  h.seq = M->seq; h.err = (unsigned long long *)M->d_window + ERR_WORD; h.timeout_ns = M->timeout_ns;
+  return h;
+}
+
+// A x + B lvec for the MatMult whose push was issued by b200_mpiaij_mult_begin: one fused launch
+// when the diagonal block runs the stream kernel, otherwise the two kernels.
+extern "C" int b200_mpiaij_mult_finish(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream)
+{
+  if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
+  if (M->fused_ok) return launch_stream_halo(M->A, d_x, d_y, mode, fused_args(M, false), (cudaStream_t)stream);
+  B200_TRY(b200_mpiaij_mult_local(M, d_x, d_y, mode, stream));
+  return b200_mpiaij_mult_end(M, d_y, mode, stream);
+}
+
 extern "C" int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream)
 {
   if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
   cudaStream_t st = (cudaStream_t)stream;
   B200_TRY(prepare_push(M));
+  if (M->fused_ok) {
+    // one launch: push CTAs + A x + B lvec (k_stream<..., HALO>)
+    M->seq += 1;
+    return launch_stream_halo(M->A, d_x, d_y, mode, fused_args(M, true), st);
+  }
   if (M->npush_blocks) {
     // fork: the push runs beside A x; join so that the caller may overwrite x afterwards
     B200_CUDA_TRY(cudaEventRecord(M->ev_fork, st));

@@ -143,12 +143,19 @@ __host__ __device__ inline size_t stream_stage_bytes(int threads, int cap)
   return (size_t)(cap + STREAM_PAD) * 12 + (size_t)(threads + 8) * 4;
 }
 
-template <int MODE, bool ADD, int THREADS>
+template <int MODE, bool ADD, int THREADS, bool HALO>
 __global__ void __launch_bounds__(THREADS + 32)
     k_stream(const int4 *__restrict__ tiles, int ntiles, const int *__restrict__ ii,
              const int *__restrict__ aj, const double *__restrict__ aa,
-             const double *__restrict__ x, const double *yin, double *y, int cap, int stages)
+             const double *__restrict__ x, const double *yin, double *y, int cap, int stages,
+             const HaloArgs h)
 {
+  // HALO (MatMult_MPIAIJ in one launch): the first h.npush CTAs are the VecScatterBegin -- they
+  // push this rank's boundary values into the peers' lvec over NVLink and leave; the stream CTAs
+  // add B*lvec to the rows of each tile that touch a ghost, after acquiring the peers' flags.
+  if (HALO && (int)blockIdx.x < h.npush) { halo_push_block(h, x, blockIdx.x); return; }
+  const int bid = HALO ? (int)blockIdx.x - h.npush : (int)blockIdx.x;
+  const int nb  = HALO ? (int)gridDim.x - h.npush : (int)gridDim.x;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full  = reinterpret_cast<uint64_t *>(smem);
   uint64_t *empty = full + stages;
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(THREADS + 32)
     if (tid == THREADS) {
       const uint64_t pol = l2_policy_evict_first();
       int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int tile = bid; tile < ntiles; tile += nb, ++it) {
         const int s = it % stages;
         if (it >= stages) mbar_wait(&empty[s], ((it / stages) - 1) & 1);
         const int4 d   = __ldg(tiles + tile);
@@ -194,8 +201,9 @@ __global__ void __launch_bounds__(THREADS + 32)
   }
 
   // --------------------------------- consumers -------------------------------------------------
-  int it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+  int  it = 0;
+  bool acquired = false;
+  for (int tile = bid; tile < ntiles; tile += nb, ++it) {
     const int  s = it % stages;
     const int4 d = __ldg(tiles + tile);
     unsigned char *st  = stage0 + (size_t)s * sbytes;
@@ -224,6 +232,21 @@ __global__ void __launch_bounds__(THREADS + 32)
           if ((k + j) < n) sum = acc<MODE>(sum, av[j], xv[j]);
       }
       y[r] = sum;
+    }
+    if (HALO) {
+      const int2 bt = __ldg(h.btiles + tile);
+      if (bt.y > bt.x) {  // uniform over the CTA: this tile has rows with ghost columns
+        if (!acquired) { if (tid == 0) halo_wait_flags(h); acquired = true; }
+        // consumer-only barrier: publishes the y stores above and the acquired flags
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+        const int c = bt.x + tid;
+        if (c < bt.y) {
+          const int lo = h.cpi[c], hi = h.cpi[c + 1], i = h.ridx[c];
+          double    sb = y[i];
+          for (int k = lo; k < hi; ++k) sb = acc<MODE>(sb, h.ba[k], __ldcg(h.lvec + h.bj[k]));
+          y[i] = sb;
+        }
+      }
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[s]);
@@ -328,7 +351,7 @@ static int dev_alloc(T **p, size_t count, b200_csr_s *A)
 template <int THREADS>
 static int stream_occupancy(size_t smem, int *ctas)
 {
-  auto kern = k_stream<B200_MODE_EXACT_FMA, false, THREADS>;  // any instantiation: same footprint
+  auto kern = k_stream<B200_MODE_EXACT_FMA, false, THREADS, false>;  // any instantiation: same footprint
   B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, kern, THREADS + 32, smem));
   return B200_OK;
 }
@@ -336,8 +359,11 @@ static int stream_occupancy(size_t smem, int *ctas)
 template <int MODE, bool ADD, int THREADS>
 static int stream_set_attr(size_t smem)
 {
-  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, ADD, THREADS>,
+  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, ADD, THREADS, false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!ADD)
+    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, false, THREADS, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return B200_OK;
 }
 
@@ -622,14 +648,45 @@ extern "C" int b200_csr_device_arrays(b200_csr_t A, const int32_t **d_ai, const 
 template <int MODE, bool ADD>
 static int launch_stream(b200_csr_s *A, const double *x, const double *yin, double *y, cudaStream_t st)
 {
+  const HaloArgs none{};
   if (A->stream_threads == 256)
-    B200_LAUNCH((k_stream<MODE, ADD, 256>), A->stream_grid, 256 + 32, A->stream_smem, st, A->d_tiles,
-                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages);
+    B200_LAUNCH((k_stream<MODE, ADD, 256, false>), A->stream_grid, 256 + 32, A->stream_smem, st, A->d_tiles,
+                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, none);
   else
-    B200_LAUNCH((k_stream<MODE, ADD, 128>), A->stream_grid, 128 + 32, A->stream_smem, st, A->d_tiles,
-                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages);
+    B200_LAUNCH((k_stream<MODE, ADD, 128, false>), A->stream_grid, 128 + 32, A->stream_smem, st, A->d_tiles,
+                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, none);
   return B200_OK;
 }
+
+// MatMult_MPIAIJ in one launch (see k_stream, HALO): push CTAs first in the grid, then the
+// persistent stream CTAs.
+template <int MODE>
+static int launch_stream_halo_mode(b200_csr_s *A, const double *x, double *y, const HaloArgs &h, cudaStream_t st)
+{
+  const int grid = h.npush + A->stream_grid;
+  if (A->stream_threads == 256)
+    B200_LAUNCH((k_stream<MODE, false, 256, true>), grid, 256 + 32, A->stream_smem, st, A->d_tiles,
+                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, nullptr, y, A->stream_cap, A->stream_stages, h);
+  else
+    B200_LAUNCH((k_stream<MODE, false, 128, true>), grid, 128 + 32, A->stream_smem, st, A->d_tiles,
+                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, nullptr, y, A->stream_cap, A->stream_stages, h);
+  return B200_OK;
+}
+
+namespace b200 {
+int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles)
+{
+  *d_tiles = A->d_tiles;
+  *ntiles  = A->kernel_override && A->kernel_override != B200_KERNEL_STREAM ? 0 : A->ntiles;
+  return B200_OK;
+}
+int launch_stream_halo(b200_csr_t A, const double *x, double *y, int mode, const HaloArgs &h, cudaStream_t st)
+{
+  if (!A->ntiles) return set_error(B200_ERR_STATE, "fused halo launch needs the stream plan");
+  if (mode == B200_MODE_EXACT) return launch_stream_halo_mode<B200_MODE_EXACT>(A, x, y, h, st);
+  return launch_stream_halo_mode<B200_MODE_EXACT_FMA>(A, x, y, h, st);
+}
+}  // namespace b200
 
 template <bool ADD>
 static int launch_vector(b200_csr_s *A, const double *x, const double *yin, double *y, cudaStream_t st)

@@ -31,7 +31,8 @@ def setup(pk, N, size):
 
 @pytest.mark.parametrize("N,size", [(12, 2), (12, 4), (16, 8), (13, 8), (10, 3), (8, 1)])
 @pytest.mark.parametrize("mode_name", ["exact", "fma"])
-def test_mpiaij_matmult_bit_exact(pk, cuda, N, size, mode_name):
+@pytest.mark.parametrize("fused", [False, True])
+def test_mpiaij_matmult_bit_exact(pk, cuda, N, size, mode_name, fused):
     torch = cuda
     mode = pk.MODE_EXACT if mode_name == "exact" else pk.MODE_EXACT_FMA
     fma = mode_name == "fma"
@@ -45,8 +46,11 @@ def test_mpiaij_matmult_bit_exact(pk, cuda, N, size, mode_name):
         for r, M in enumerate(ranks):
             M.mult_begin(xs[r])
         for r, M in enumerate(ranks):
-            M.mult_local(xs[r], ys[r], mode)
-            M.mult_end(ys[r], mode)
+            if fused:   # A x and B lvec in one launch (the kernel b200_mpiaij_mult uses)
+                M.mult_finish(xs[r], ys[r], mode)
+            else:
+                M.mult_local(xs[r], ys[r], mode)
+                M.mult_end(ys[r], mode)
         torch.cuda.synchronize()
         for r, M in enumerate(ranks):
             M.check()
