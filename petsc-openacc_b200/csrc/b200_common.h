@@ -60,7 +60,8 @@ struct HaloArgs {
   unsigned        *done;
   int              npush;
   // receive side (VecScatterEnd + MatMultAdd of the off-diagonal block, compressed row)
-  const int2      *btiles;     // per stream tile: [first, last) position in the compressed-row index
+  const int       *cta_ptr;    // per stream CTA: [first, last) in cta_rows
+  const int       *cta_rows;   // compressed-row positions of B grouped by the CTA that owns the row's tile
   const int       *cpi, *ridx, *bj;
   const double    *ba;
   const double    *lvec;
@@ -72,7 +73,7 @@ struct HaloArgs {
   unsigned long long  timeout_ns;
 };
 // internal (not part of the C ABI): the stream plan of a matrix and the fused launch
-int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles);   // 0 tiles = not applicable
+int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid);   // 0 tiles = not applicable
 int launch_stream_halo(b200_csr_t A, const double *x, double *y, int mode, const HaloArgs &h,
                        cudaStream_t st);
 

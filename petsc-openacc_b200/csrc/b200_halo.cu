@@ -28,7 +28,7 @@ namespace {
 constexpr int    WINDOW_HDR_BYTES = 1024;
 constexpr int    MAX_RANKS        = 120;
 constexpr int    ERR_WORD         = 126;
-constexpr int    PUSH_CHUNK       = 2048;  // elements per CTA of the push kernel
+constexpr int    PUSH_CHUNK       = 2304;  // elements per CTA of the push role (8 per thread of a 288-thread CTA)
 
 // VecScatterBegin: gather x[send_idx] and store it into each peer's lvec (peer memory), then the
 // last CTA of each peer releases flag = seq.
@@ -106,7 +106,8 @@ struct b200_mpiaij_s {
   double *d_hx = nullptr, *d_hy = nullptr;
   cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
   unsigned long long timeout_ns = 2000ull * 1000000ull;
-  int2 *d_btiles = nullptr;   // fused launch: compressed-row range of B per stream tile of A
+  int *d_cta_ptr = nullptr, *d_cta_rows = nullptr;  // fused launch: B rows grouped by owning CTA
+  int   fused_grid = 0;
   bool  fused_ok = false;
 };
 
@@ -172,7 +173,7 @@ extern "C" int b200_mpiaij_destroy(b200_mpiaij_t M)
   if (M->A) b200_csr_destroy(M->A);
   if (M->B) b200_csr_destroy(M->B);
   cudaFree(M->d_cpi); cudaFree(M->d_ridx); cudaFree(M->d_bj); cudaFree(M->d_ba); cudaFree(M->d_srcs);
-  cudaFree(M->d_btiles);
+  cudaFree(M->d_cta_ptr); cudaFree(M->d_cta_rows);
   cudaFree(M->d_send_idx); cudaFree(M->d_window); cudaFree(M->d_blocks); cudaFree(M->d_peers); cudaFree(M->d_done);
   if (M->side) cudaStreamDestroy(M->side);
   if (M->hstream) cudaStreamDestroy(M->hstream);
@@ -273,23 +274,28 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
   B200_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_fork, cudaEventDisableTiming));
   B200_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_join, cudaEventDisableTiming));
   M->timeout_ns = (unsigned long long)env_int("B200_MPIAIJ_TIMEOUT_MS", 2000) * 1000000ull;
-  // fused launch: for every stream tile of A, the run of B's compressed rows inside it
+  // fused launch: group B's compressed rows by the stream CTA that owns the tile of the row
+  // (tile t belongs to CTA t % grid), so that each CTA finishes exactly the rows it wrote
   {
     int4 *d_tiles = nullptr;
-    int   ntiles  = 0;
-    B200_TRY(stream_plan_tiles(M->A, &d_tiles, &ntiles));
-    if (ntiles && env_int("B200_MPIAIJ_FUSED", 1)) {
+    int   ntiles = 0, grid = 0;
+    B200_TRY(stream_plan_tiles(M->A, &d_tiles, &ntiles, &grid));
+    if (ntiles && grid > 0 && env_int("B200_MPIAIJ_FUSED", 1)) {
       std::vector<int4> tiles((size_t)ntiles);
       B200_CUDA_TRY(cudaMemcpy(tiles.data(), d_tiles, sizeof(int4) * (size_t)ntiles, cudaMemcpyDeviceToHost));
-      std::vector<int2> bt((size_t)ntiles);
-      size_t c = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        while (c < M->ridx.size() && M->ridx[c] < tiles[t].x) ++c;
-        bt[t].x = (int)c;
-        while (c < M->ridx.size() && M->ridx[c] < tiles[t].y) ++c;
-        bt[t].y = (int)c;
+      std::vector<int> owner(M->ridx.size()), ptr((size_t)grid + 1, 0), rows(M->ridx.size());
+      int t = 0;
+      for (size_t c = 0; c < M->ridx.size(); ++c) {
+        while (t < ntiles && M->ridx[c] >= tiles[t].y) ++t;
+        owner[c] = t % grid;
+        ptr[owner[c] + 1]++;
       }
-      B200_TRY(up(&M->d_btiles, bt));
+      for (int b = 0; b < grid; ++b) ptr[b + 1] += ptr[b];
+      std::vector<int> next(ptr.begin(), ptr.end() - 1);
+      for (size_t c = 0; c < M->ridx.size(); ++c) rows[next[owner[c]]++] = (int)c;
+      B200_TRY(up(&M->d_cta_ptr, ptr));
+      B200_TRY(up(&M->d_cta_rows, rows));
+      M->fused_grid = grid;
       M->fused_ok = true;
     }
   }
@@ -427,7 +433,7 @@ static HaloArgs fused_args(b200_mpiaij_s *M, bool with_push)
   HaloArgs h{};
   h.blocks = M->d_blocks; h.peers = M->d_peers; h.send_idx = M->d_send_idx; h.done = M->d_done;
   h.npush = with_push ? M->npush_blocks : 0;
-  h.btiles = M->d_btiles; h.cpi = M->d_cpi; h.ridx = M->d_ridx; h.bj = M->d_bj; h.ba = M->d_ba;
+  h.cta_ptr = M->d_cta_ptr; h.cta_rows = M->d_cta_rows; h.cpi = M->d_cpi; h.ridx = M->d_ridx; h.bj = M->d_bj; h.ba = M->d_ba;
   h.lvec = (const double *)(M->d_window + WINDOW_HDR_BYTES) + (size_t)(M->seq & 1) * M->ngpad;
   h.flags = (const unsigned long long *)M->d_window; h.srcs = M->d_srcs; h.nsrc = (int)M->srcs.size();
   h.seq = M->seq; h.err = (unsigned long long *)M->d_window + ERR_WORD; h.timeout_ns = M->timeout_ns;
@@ -449,8 +455,8 @@ extern "C" int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y,
   if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
   cudaStream_t st = (cudaStream_t)stream;
   B200_TRY(prepare_push(M));
-  if (M->fused_ok) {
-    // one launch: push CTAs + A x + B lvec (k_stream<..., HALO>)
+  if (M->fused_ok && M->npush_blocks <= M->fused_grid) {
+    // one launch: push prologue + A x + B lvec (k_stream<..., HALO>)
     M->seq += 1;
     return launch_stream_halo(M->A, d_x, d_y, mode, fused_args(M, true), st);
   }

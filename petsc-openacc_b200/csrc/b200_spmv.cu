@@ -150,12 +150,14 @@ __global__ void __launch_bounds__(THREADS + 32)
              const double *__restrict__ x, const double *yin, double *y, int cap, int stages,
              const HaloArgs h)
 {
-  // HALO (MatMult_MPIAIJ in one launch): the first h.npush CTAs are the VecScatterBegin -- they
-  // push this rank's boundary values into the peers' lvec over NVLink and leave; the stream CTAs
-  // add B*lvec to the rows of each tile that touch a ghost, after acquiring the peers' flags.
-  if (HALO && (int)blockIdx.x < h.npush) { halo_push_block(h, x, blockIdx.x); return; }
-  const int bid = HALO ? (int)blockIdx.x - h.npush : (int)blockIdx.x;
-  const int nb  = HALO ? (int)gridDim.x - h.npush : (int)gridDim.x;
+  // HALO (MatMult_MPIAIJ in one launch): the first h.npush CTAs start with the VecScatterBegin --
+  // they push this rank's boundary values into the peers' lvec over NVLink -- and then stream
+  // tiles like every other CTA.  After its last tile a CTA acquires the peers' flags (by then the
+  // ghost values have long arrived: the wait is off the critical path) and adds B*lvec to the
+  // ghost-touching rows of the tiles it owns.
+  if (HALO && (int)blockIdx.x < h.npush) halo_push_block(h, x, blockIdx.x);
+  const int bid = (int)blockIdx.x;
+  const int nb  = (int)gridDim.x;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full  = reinterpret_cast<uint64_t *>(smem);
   uint64_t *empty = full + stages;
@@ -201,8 +203,7 @@ __global__ void __launch_bounds__(THREADS + 32)
   }
 
   // --------------------------------- consumers -------------------------------------------------
-  int  it = 0;
-  bool acquired = false;
+  int it = 0;
   for (int tile = bid; tile < ntiles; tile += nb, ++it) {
     const int  s = it % stages;
     const int4 d = __ldg(tiles + tile);
@@ -233,23 +234,29 @@ __global__ void __launch_bounds__(THREADS + 32)
       }
       y[r] = sum;
     }
-    if (HALO) {
-      const int2 bt = __ldg(h.btiles + tile);
-      if (bt.y > bt.x) {  // uniform over the CTA: this tile has rows with ghost columns
-        if (!acquired) { if (tid == 0) halo_wait_flags(h); acquired = true; }
-        // consumer-only barrier: publishes the y stores above and the acquired flags
-        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
-        const int c = bt.x + tid;
-        if (c < bt.y) {
-          const int lo = h.cpi[c], hi = h.cpi[c + 1], i = h.ridx[c];
-          double    sb = y[i];
-          for (int k = lo; k < hi; ++k) sb = acc<MODE>(sb, h.ba[k], __ldcg(h.lvec + h.bj[k]));
-          y[i] = sb;
-        }
-      }
-    }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+  }
+  if (HALO) {
+    // VecScatterEnd + MatMultAdd(B, lvec, y, y) for the tiles of this CTA.  One lane per source
+    // rank acquires that rank's flag; the consumer-only barrier publishes the flags and this
+    // CTA's y stores.  cta_rows lists the ghost-touching rows of the tiles this CTA owns.
+    if (tid < h.nsrc) {
+      const unsigned long long t0 = globaltimer_ns();
+      const unsigned long long *f = h.flags + h.srcs[tid];
+      while (ld_acquire_sys(f) < h.seq) {
+        if (globaltimer_ns() - t0 > h.timeout_ns) { atomicExch(h.err, 1ull); break; }
+        __nanosleep(32);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+    for (int q = h.cta_ptr[bid] + tid; q < h.cta_ptr[bid + 1]; q += THREADS) {
+      const int c  = h.cta_rows[q];
+      const int lo = h.cpi[c], hi = h.cpi[c + 1], i = h.ridx[c];
+      double    sb = y[i];
+      for (int k = lo; k < hi; ++k) sb = acc<MODE>(sb, h.ba[k], __ldcg(h.lvec + h.bj[k]));
+      y[i] = sb;
+    }
   }
 }
 
@@ -663,7 +670,8 @@ static int launch_stream(b200_csr_s *A, const double *x, const double *yin, doub
 template <int MODE>
 static int launch_stream_halo_mode(b200_csr_s *A, const double *x, double *y, const HaloArgs &h, cudaStream_t st)
 {
-  const int grid = h.npush + A->stream_grid;
+  const int grid = A->stream_grid;  // cta_ptr/cta_rows were built for exactly this grid
+  if (h.npush > grid) return set_error(B200_ERR_STATE, "more push blocks (%d) than CTAs (%d)", h.npush, grid);
   if (A->stream_threads == 256)
     B200_LAUNCH((k_stream<MODE, false, 256, true>), grid, 256 + 32, A->stream_smem, st, A->d_tiles,
                 A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, nullptr, y, A->stream_cap, A->stream_stages, h);
@@ -674,9 +682,10 @@ static int launch_stream_halo_mode(b200_csr_s *A, const double *x, double *y, co
 }
 
 namespace b200 {
-int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles)
+int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid)
 {
   *d_tiles = A->d_tiles;
+  *grid    = A->stream_grid;
   *ntiles  = A->kernel_override && A->kernel_override != B200_KERNEL_STREAM ? 0 : A->ntiles;
   return B200_OK;
 }
