@@ -323,6 +323,7 @@ struct b200_csr_s {
   int    *d_cpi = nullptr, *d_ridx = nullptr;
   // stream plan
   int4   *d_tiles = nullptr;
+  std::vector<int4> h_tiles;
   int32_t ntiles = 0, stream_threads = 256, stream_cap = 0, stream_stages = 0, stream_grid = 0;
   size_t  stream_smem = 0;
   // vector plan
@@ -335,6 +336,10 @@ struct b200_csr_s {
   size_t       hx_len = 0, hy_len = 0;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t  hev[2] = {nullptr, nullptr};
+  // row-blocked pipeline of the host-vector path (tile-aligned blocks of ~1M rows)
+  std::vector<int>         pb_tile;   // block b = tiles [pb_tile[b], pb_tile[b+1])
+  std::vector<int>         pb_need;   // last x chunk block b reads (chunks = the same row blocks)
+  std::vector<cudaEvent_t> pb_evx, pb_evk;
   uint64_t     device_bytes = 0;
 };
 
@@ -465,6 +470,7 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
     }
     if (stream_ok) {
       A->ntiles = (int)tiles.size();
+      A->h_tiles = tiles;
       A->stream_threads = threads;
       A->stream_cap     = cap;
       A->stream_stages  = stages;
@@ -496,6 +502,37 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
   else if (mean >= 2.0) A->kernel_fast = B200_KERNEL_VECTOR;
   else A->kernel_fast = B200_KERNEL_ROW;
   return B200_OK;
+}
+
+// Row blocks for the pipelined host-vector path: tile-aligned, about B200_HOST_BLOCK_ROWS rows
+// each (default 2^20; the reference's step 4 uses 983,040, src/openacc-step4/MatMult_SeqAIJ.patch:51).
+// need[b] = the x chunk that holds the largest column any row of block b touches; columns ascend
+// inside a row, so that is the last entry of each row.
+static void build_host_blocks(b200_csr_s *A, const int32_t *ai, const int32_t *aj, const std::vector<int4> &tiles)
+{
+  A->pb_tile.clear(); A->pb_need.clear();
+  if (A->ntiles < 2 || A->m != A->n || !aj) return;
+  const int target = std::max(1024, env_int("B200_HOST_BLOCK_ROWS", 1 << 20));
+  A->pb_tile.push_back(0);
+  int rows = 0;
+  for (int t = 0; t < A->ntiles; ++t) {
+    rows += tiles[t].y - tiles[t].x;
+    if (rows >= target && t + 1 < A->ntiles) { A->pb_tile.push_back(t + 1); rows = 0; }
+  }
+  A->pb_tile.push_back(A->ntiles);
+  const int nblk = (int)A->pb_tile.size() - 1;
+  if (nblk < 2) { A->pb_tile.clear(); return; }
+  std::vector<int> rowend(nblk);
+  for (int b = 0; b < nblk; ++b) rowend[b] = tiles[A->pb_tile[b + 1] - 1].y;
+  A->pb_need.resize(nblk);
+  for (int b = 0; b < nblk; ++b) {
+    const int r0 = tiles[A->pb_tile[b]].x, r1 = rowend[b];
+    int cmax = -1;
+    for (int r = r0; r < r1; ++r) if (ai[r + 1] > ai[r]) cmax = std::max(cmax, aj[ai[r + 1] - 1]);
+    int j = 0;
+    while (j < nblk - 1 && rowend[j] <= cmax) ++j;
+    A->pb_need[b] = j;
+  }
 }
 
 static int create_common(b200_csr_s *A, const int32_t *h_ai)
@@ -559,7 +596,9 @@ extern "C" int b200_csr_create(b200_csr_t *out, int32_t m, int32_t n, const int3
       B200_CUDA_TRY(cudaMemcpy(A->d_aj, h_aj, (size_t)nz * sizeof(int), cudaMemcpyHostToDevice));
       B200_CUDA_TRY(cudaMemcpy(A->d_aa, h_aa, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice));
     }
-    return create_common(A, h_ai);
+    B200_TRY(create_common(A, h_ai));
+    if (A->ntiles) build_host_blocks(A, h_ai, h_aj, A->h_tiles);
+    return B200_OK;
   }();
   if (rc) { b200_csr_destroy(A); return rc; }
   *out = A;
@@ -610,6 +649,8 @@ extern "C" int b200_csr_destroy(b200_csr_t A)
   cudaFree(A->d_hx); cudaFree(A->d_hy);
   for (auto &s : A->hs) if (s) cudaStreamDestroy(s);
   for (auto &e : A->hev) if (e) cudaEventDestroy(e);
+  for (auto &e : A->pb_evx) if (e) cudaEventDestroy(e);
+  for (auto &e : A->pb_evk) if (e) cudaEventDestroy(e);
   delete A;
   return B200_OK;
 }
@@ -662,6 +703,21 @@ static int launch_stream(b200_csr_s *A, const double *x, const double *yin, doub
   else
     B200_LAUNCH((k_stream<MODE, ADD, 128, false>), A->stream_grid, 128 + 32, A->stream_smem, st, A->d_tiles,
                 A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, none);
+  return B200_OK;
+}
+
+// tiles [t0, t0 + nt) only: the row-blocked host pipeline
+template <int MODE, bool ADD>
+static int launch_stream_range(b200_csr_s *A, int t0, int nt, const double *x, const double *yin, double *y, cudaStream_t st)
+{
+  const HaloArgs none{};
+  const int grid = std::min(nt, A->stream_grid);
+  if (A->stream_threads == 256)
+    B200_LAUNCH((k_stream<MODE, ADD, 256, false>), grid, 256 + 32, A->stream_smem, st, A->d_tiles + t0,
+                nt, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, none);
+  else
+    B200_LAUNCH((k_stream<MODE, ADD, 128, false>), grid, 128 + 32, A->stream_smem, st, A->d_tiles + t0,
+                nt, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, none);
   return B200_OK;
 }
 
@@ -865,11 +921,62 @@ static int host_scratch(b200_csr_s *A, size_t nx, size_t ny)
   return B200_OK;
 }
 
+// Row-blocked pipeline: x chunks go up on stream 0, block b's tiles run on stream 1 as soon as
+// the last chunk it reads has landed, its y rows go down on stream 2 -- uploads, kernels and
+// downloads of different blocks overlap (PCIe is full duplex).  Banded matrices only need a
+// look-ahead of the bandwidth; for others need[b] is the last chunk and only the downloads overlap.
+static int spmv_host_pipelined(b200_csr_s *A, const double *h_x, const double *h_yin, double *h_y, int mode)
+{
+  const int nblk = (int)A->pb_tile.size() - 1;
+  if ((int)A->pb_evx.size() < nblk) {
+    const size_t old = A->pb_evx.size();
+    A->pb_evx.resize(nblk); A->pb_evk.resize(nblk);
+    for (size_t b = old; b < (size_t)nblk; ++b) {
+      B200_CUDA_TRY(cudaEventCreateWithFlags(&A->pb_evx[b], cudaEventDisableTiming));
+      B200_CUDA_TRY(cudaEventCreateWithFlags(&A->pb_evk[b], cudaEventDisableTiming));
+    }
+  }
+  auto r0 = [&](int b) { return A->h_tiles[A->pb_tile[b]].x; };
+  auto r1 = [&](int b) { return A->h_tiles[A->pb_tile[b + 1] - 1].y; };
+  for (int b = 0; b < nblk; ++b) {
+    const size_t off = r0(b), len = (size_t)r1(b) - r0(b);
+    B200_CUDA_TRY(cudaMemcpyAsync(A->d_hx + off, h_x + off, len * sizeof(double), cudaMemcpyHostToDevice, A->hs[0]));
+    if (h_yin) B200_CUDA_TRY(cudaMemcpyAsync(A->d_hy + off, h_yin + off, len * sizeof(double), cudaMemcpyHostToDevice, A->hs[0]));
+    B200_CUDA_TRY(cudaEventRecord(A->pb_evx[b], A->hs[0]));
+  }
+  for (int b = 0; b < nblk; ++b) {
+    B200_CUDA_TRY(cudaStreamWaitEvent(A->hs[1], A->pb_evx[std::max(A->pb_need[b], b)], 0));
+    const int t0 = A->pb_tile[b], nt = A->pb_tile[b + 1] - t0;
+    if (h_yin) {
+      if (mode == B200_MODE_EXACT) B200_TRY((launch_stream_range<B200_MODE_EXACT, true>(A, t0, nt, A->d_hx, A->d_hy, A->d_hy, A->hs[1])));
+      else B200_TRY((launch_stream_range<B200_MODE_EXACT_FMA, true>(A, t0, nt, A->d_hx, A->d_hy, A->d_hy, A->hs[1])));
+    } else {
+      if (mode == B200_MODE_EXACT) B200_TRY((launch_stream_range<B200_MODE_EXACT, false>(A, t0, nt, A->d_hx, nullptr, A->d_hy, A->hs[1])));
+      else B200_TRY((launch_stream_range<B200_MODE_EXACT_FMA, false>(A, t0, nt, A->d_hx, nullptr, A->d_hy, A->hs[1])));
+    }
+    B200_CUDA_TRY(cudaEventRecord(A->pb_evk[b], A->hs[1]));
+    B200_CUDA_TRY(cudaStreamWaitEvent(A->hs[2], A->pb_evk[b], 0));
+    const size_t off = r0(b), len = (size_t)r1(b) - r0(b);
+    B200_CUDA_TRY(cudaMemcpyAsync(h_y + off, A->d_hy + off, len * sizeof(double), cudaMemcpyDeviceToHost, A->hs[2]));
+  }
+  B200_CUDA_TRY(cudaStreamSynchronize(A->hs[2]));
+  B200_CUDA_TRY(cudaStreamSynchronize(A->hs[0]));
+  return B200_OK;
+}
+
+static bool host_pipeline_applies(b200_csr_s *A, int mode)
+{
+  if (A->pb_tile.size() < 3 || !env_int("B200_HOST_PIPELINE", 1)) return false;
+  const int kernel = A->kernel_override ? A->kernel_override : (mode == B200_MODE_FAST ? A->kernel_fast : A->kernel_exact);
+  return kernel == B200_KERNEL_STREAM;
+}
+
 extern "C" int b200_spmv_host(b200_csr_t A, const double *h_x, double *h_y, int mode)
 {
   if (!A || (!h_x && A->n) || (!h_y && A->m)) return set_error(B200_ERR_ARG, "b200_spmv_host: null argument");
   B200_TRY(check_mode(mode));
   B200_TRY(host_scratch(A, A->n, A->m));
+  if (host_pipeline_applies(A, mode)) return spmv_host_pipelined(A, h_x, nullptr, h_y, mode);
   cudaStream_t s = A->hs[0];
   B200_CUDA_TRY(cudaMemcpyAsync(A->d_hx, h_x, (size_t)A->n * sizeof(double), cudaMemcpyHostToDevice, s));
   B200_TRY(spmv_dispatch<false>(A, A->d_hx, nullptr, A->d_hy, mode, s));
@@ -883,6 +990,7 @@ extern "C" int b200_spmv_add_host(b200_csr_t A, const double *h_x, const double 
   if (!A || (!h_x && A->n) || ((!h_y || !h_z) && A->m)) return set_error(B200_ERR_ARG, "b200_spmv_add_host: null argument");
   B200_TRY(check_mode(mode));
   B200_TRY(host_scratch(A, A->n, A->m));
+  if (host_pipeline_applies(A, mode)) return spmv_host_pipelined(A, h_x, h_y, h_z, mode);
   cudaStream_t s = A->hs[0];
   B200_CUDA_TRY(cudaMemcpyAsync(A->d_hx, h_x, (size_t)A->n * sizeof(double), cudaMemcpyHostToDevice, s));
   B200_CUDA_TRY(cudaMemcpyAsync(A->d_hy, h_y, (size_t)A->m * sizeof(double), cudaMemcpyHostToDevice, s));
