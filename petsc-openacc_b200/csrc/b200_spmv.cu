@@ -260,6 +260,70 @@ __global__ void __launch_bounds__(THREADS + 32)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_merge: nnz-balanced tiles for skewed row lengths (power-law matrices).  A tile is a run of at
+// most MERGE_CAP consecutive non-zeros and at most MERGE_RCAP rows; long rows are split across
+// tiles.  Phase 1: the CTA forms all products of its run, coalesced over non-zeros, into shared
+// memory.  Phase 2: a segmented reduction with L = 1..32 lanes per row (L chosen per tile from its
+// row count, so a tile holding one 2048-entry row and a tile holding 600 short rows are both
+// busy).  Rows completed inside the tile are stored; the head / tail partial of a split row goes
+// to head[tile] / tail[tile] and k_merge_fixup adds them in tile order -- no atomics, so the
+// result is the same from run to run.
+// tiles[t] = {first row, last row + 1, first nnz, last nnz + 1}.
+// ---------------------------------------------------------------------------------------------
+#define MERGE_CAP 2048
+#define MERGE_RCAP 1024
+#define MERGE_THREADS 256
+
+template <bool ADD>
+__global__ void __launch_bounds__(MERGE_THREADS)
+    k_merge(const int4 *__restrict__ tiles, const int *__restrict__ ii, const int *__restrict__ aj,
+            const double *__restrict__ aa, const double *__restrict__ x, const double *yin,
+            double *y, double *head, double *tail)
+{
+  __shared__ double prod[MERGE_CAP];
+  __shared__ int    rp[MERGE_RCAP + 1];
+  const int4 d   = __ldg(tiles + blockIdx.x);
+  const int  tid = threadIdx.x, nr = d.y - d.x, s = d.z, e = d.w;
+  for (int j = tid; j <= nr; j += MERGE_THREADS) rp[j] = min(max(__ldg(ii + d.x + j), s), e) - s;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  for (int k = tid; k < e - s; k += MERGE_THREADS)
+    prod[k] = ldg_f64_stream_policy(aa + s + k, pol_stream) * ldg_f64_policy(x + ldg_s32_stream_policy(aj + s + k, pol_stream), pol_keep);
+  __syncthreads();
+  int L = 1;
+  while (L < 32 && L * nr * 2 <= MERGE_THREADS) L <<= 1;   // lanes per row, uniform over the CTA
+  const int lane = tid & (L - 1), slot = tid / L, slots = MERGE_THREADS / L;
+  for (int jb = 0; jb < nr; jb += slots) {
+    const int j   = jb + slot;
+    double    sum = 0.0;
+    if (j < nr)
+      for (int k = rp[j] + lane; k < rp[j + 1]; k += L) sum += prod[k];
+    for (int off = L >> 1; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (j < nr && lane == 0) {
+      const int  r         = d.x + j;
+      const bool head_part = (j == 0) && (__ldg(ii + r) < s);
+      const bool tail_part = (j == nr - 1) && (__ldg(ii + r + 1) > e);
+      if (!head_part && !tail_part) y[r] = ADD ? yin[r] + sum : sum;
+      else if (head_part) head[blockIdx.x] = sum;   // also the "whole tile inside one row" case
+      else tail[blockIdx.x] = sum;
+    }
+  }
+}
+
+// split[q] = {row, first tile, last tile}: y[row] = tail[first] + head[first+1..last]
+template <bool ADD>
+__global__ void k_merge_fixup(int nsplit, const int4 *__restrict__ split, const double *__restrict__ head,
+                              const double *__restrict__ tail, const double *yin, double *y)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nsplit) return;
+  const int4 sp  = split[q];
+  double     sum = tail[sp.y];
+  for (int t = sp.y + 1; t <= sp.z; ++t) sum += head[t];
+  y[sp.x] = ADD ? yin[sp.x] + sum : sum;
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_cprow: compressed-row MatMultAdd / MatMult [P376 MatMult_SeqAIJ compressed branch]: only the
 // cprow.nrows non-empty rows are touched (the off-diagonal block B has ~2% non-empty rows).
@@ -326,6 +390,10 @@ struct b200_csr_s {
   std::vector<int4> h_tiles;
   int32_t ntiles = 0, stream_threads = 256, stream_cap = 0, stream_stages = 0, stream_grid = 0;
   size_t  stream_smem = 0;
+  // merge plan
+  int4   *d_mtiles = nullptr, *d_msplit = nullptr;
+  double *d_mhead = nullptr, *d_mtail = nullptr;
+  int32_t nmtiles = 0, nmsplit = 0;
   // vector plan
   int32_t vector_lanes = 8;
   int32_t kernel_fast = B200_KERNEL_ROW, kernel_exact = B200_KERNEL_ROW, kernel_override = 0;
@@ -398,6 +466,53 @@ static int stream_set_all_attrs(int /*threads*/, size_t /*smem*/)
   return B200_OK;
 }
 
+// Tiles of the merge kernel: greedy over rows; a row is split only when it cannot fit a fresh
+// tile or the current tile is less than half full.
+static int build_merge_plan(b200_csr_s *A, const int32_t *ai)
+{
+  const int m = A->m;
+  std::vector<int4> tiles, split;
+  int r = 0, pos = 0;
+  int open_row = -1, open_first = -1;  // a row whose tail is still being emitted
+  while (r < m) {
+    const int s = pos, r0 = r, cap_end = s + MERGE_CAP;
+    int rr = r;
+    while (rr < m && ai[rr + 1] <= cap_end && (rr - r0) < MERGE_RCAP) ++rr;
+    int e, r1, split_row = -1;
+    const bool more  = rr < m && (rr - r0) < MERGE_RCAP;
+    const int  used  = (rr > r0 ? ai[rr] : s) - s;
+    const int  start = more ? std::max(ai[rr], s) : 0;  // where row rr would begin inside this tile
+    if (more && start < cap_end && ai[rr + 1] > cap_end && (used * 2 < MERGE_CAP || ai[rr + 1] - start > MERGE_CAP)) {
+      e = cap_end; r1 = rr + 1; split_row = rr;   // row rr continues in the next tile
+    } else {
+      if (rr == r0) return set_error(B200_ERR_STATE, "merge plan made no progress at row %d", r0);
+      e = ai[rr]; r1 = rr;
+    }
+    r = rr; pos = e;
+    const int t = (int)tiles.size();
+    tiles.push_back(make_int4(r0, r1, s, e));
+    // 1. a row split earlier ends here when it is this tile's first row and is complete in it
+    if (open_row >= 0 && open_row == r0 && open_first < t && ai[r0 + 1] <= e) {
+      split.push_back(make_int4(open_row, open_first, t, 0));
+      open_row = -1;
+    }
+    // 2. a row whose first piece is in this tile
+    if (split_row >= 0 && open_row != split_row) { open_row = split_row; open_first = t; }
+  }
+  A->nmtiles = (int)tiles.size();
+  A->nmsplit = (int)split.size();
+  if (!A->nmtiles) return B200_OK;
+  B200_TRY(dev_alloc(&A->d_mtiles, tiles.size(), A));
+  B200_TRY(dev_alloc(&A->d_msplit, split.size(), A));
+  B200_TRY(dev_alloc(&A->d_mhead, tiles.size(), A));
+  B200_TRY(dev_alloc(&A->d_mtail, tiles.size(), A));
+  B200_CUDA_TRY(cudaMemcpy(A->d_mtiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if (!split.empty()) B200_CUDA_TRY(cudaMemcpy(A->d_msplit, split.data(), split.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  B200_CUDA_TRY(cudaMemset(A->d_mhead, 0, tiles.size() * sizeof(double)));
+  B200_CUDA_TRY(cudaMemset(A->d_mtail, 0, tiles.size() * sizeof(double)));
+  return B200_OK;
+}
+
 // Build the plan from the host row-pointer array.
 static int build_plan(b200_csr_s *A, const int32_t *ai)
 {
@@ -433,15 +548,35 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
   }
   // --- stream tiles ---------------------------------------------------------------------------
   const double mean = A->nonzerorowcnt ? (double)A->nz / A->nonzerorowcnt : 0.0;
-  int threads = env_int("B200_STREAM_THREADS", mean <= 12.0 ? 256 : 128);
-  if (threads != 128 && threads != 256) threads = 256;
+  // Stream configuration.  Measured on B200 (profiles/r01_sweep_*.log): the x gather is latency
+  // bound, so throughput follows the number of RESIDENT consumer threads per SM until ~1024, where
+  // HBM saturates.  Pick (threads per CTA, ring depth) that maximises resident consumers; prefer
+  // the 2-deep ring once 1024 are reached (7-point: 256 x 2 stages x 4 CTAs; 27-point: 128 x 1
+  // stage x 5 CTAs).  B200_STREAM_* environment variables override for sweeps.
+  B200_TRY(stream_set_all_attrs(0, 0));  // opt in to > 48 KB before asking for occupancy
+  int threads = env_int("B200_STREAM_THREADS", 0), stages = env_int("B200_STREAM_STAGES", 0);
   int cap = env_int("B200_STREAM_CAP", 0);
-  if (cap <= 0) {
-    cap = (int)(threads * std::max(mean, 1.0) * 1.05) + 32;
-    cap = std::min(cap, 8192);
+  auto cap_for = [&](int T) { return std::max(((std::min((int)(T * std::max(mean, 1.0) * 1.05) + 32, 8192) + 3) & ~3), 64); };
+  if ((threads != 128 && threads != 256) || stages <= 0) {
+    long best = -1;
+    int  bt = 256, bs = 2;
+    for (int T : {256, 128}) {
+      if (threads == 128 || threads == 256) { if (T != threads) continue; }
+      for (int S : {2, 1}) {
+        if (stages > 0 && S != stages) continue;
+        const size_t smem = 128 + (size_t)S * stream_stage_bytes(T, cap > 0 ? ((cap + 3) & ~3) : cap_for(T));
+        if (smem > 227 * 1024) continue;
+        int ctas = 0;
+        if (T == 256) B200_TRY(stream_occupancy<256>(smem, &ctas)); else B200_TRY(stream_occupancy<128>(smem, &ctas));
+        const long thr = (long)ctas * T, score = std::min(thr, 1024L) * 4 + (S == 2 ? 2 : 0) + (T == 256 ? 1 : 0);
+        if (score > best) { best = score; bt = T; bs = S; }
+      }
+    }
+    if (threads != 128 && threads != 256) threads = bt;
+    if (stages <= 0) stages = bs;
   }
+  if (cap <= 0) cap = cap_for(threads);
   cap = std::max((cap + 3) & ~3, 64);
-  int stages = env_int("B200_STREAM_STAGES", 0);
   A->ntiles  = 0;
   bool stream_ok = (m > 0 && A->nz > 0 && A->rmax <= cap);
   if (stream_ok) {
@@ -460,9 +595,6 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
     }
     if (stream_ok) {
       const size_t sbytes = stream_stage_bytes(threads, cap);
-      // Measured on B200 (profiles/r01_sweep_*.log): throughput follows the number of resident
-      // consumer threads (the x gather is latency bound), so prefer a short ring and many CTAs.
-      if (stages <= 0) stages = 2;
       stages = std::min(std::max(stages, 1), 8);
       A->stream_smem = 128 + (size_t)stages * sbytes;
       if (A->stream_smem > 227 * 1024) { stages = 1; A->stream_smem = 128 + sbytes; }
@@ -499,8 +631,11 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
   const bool regular = A->rmax <= std::max(32.0, 4.0 * mean);
   if (A->cprow_use) A->kernel_fast = B200_KERNEL_CPROW;
   else if (A->ntiles && regular) A->kernel_fast = B200_KERNEL_STREAM;
-  else if (mean >= 2.0) A->kernel_fast = B200_KERNEL_VECTOR;
-  else A->kernel_fast = B200_KERNEL_ROW;
+  else if (A->nz > 0) {
+    // skewed row lengths: nnz-balanced merge tiles
+    B200_TRY(build_merge_plan(A, ai));
+    A->kernel_fast = A->nmtiles ? B200_KERNEL_MERGE : B200_KERNEL_VECTOR;
+  } else A->kernel_fast = B200_KERNEL_ROW;
   return B200_OK;
 }
 
@@ -646,6 +781,7 @@ extern "C" int b200_csr_destroy(b200_csr_t A)
   if (A->T) b200_csr_destroy(A->T);
   cudaFree(A->d_ai); cudaFree(A->d_aj); cudaFree(A->d_aa);
   cudaFree(A->d_cpi); cudaFree(A->d_ridx); cudaFree(A->d_tiles);
+  cudaFree(A->d_mtiles); cudaFree(A->d_msplit); cudaFree(A->d_mhead); cudaFree(A->d_mtail);
   cudaFree(A->d_hx); cudaFree(A->d_hy);
   for (auto &s : A->hs) if (s) cudaStreamDestroy(s);
   for (auto &e : A->hev) if (e) cudaEventDestroy(e);
@@ -664,7 +800,7 @@ extern "C" int b200_csr_get_info(b200_csr_t A, b200_csr_info_t *info)
   info->compressedrow_use = A->cprow_use; info->cprow_nrows = A->cprow_nrows;
   info->kernel_fast = A->kernel_fast; info->kernel_exact = A->kernel_exact;
   info->vector_lanes = A->vector_lanes; info->stream_tiles = A->ntiles;
-  info->merge_tiles = 0; info->has_transpose = A->T != nullptr;
+  info->merge_tiles = A->nmtiles; info->has_transpose = A->T != nullptr;
   memcpy(info->hist, A->hist, sizeof A->hist);
   info->device_bytes = A->device_bytes + (A->T ? A->T->device_bytes : 0);
   return B200_OK;
@@ -675,7 +811,12 @@ extern "C" int b200_csr_set_kernel(b200_csr_t A, int kernel)
   if (!A || kernel < 0 || kernel > B200_KERNEL_CPROW) return set_error(B200_ERR_ARG, "b200_csr_set_kernel: bad argument");
   if (kernel == B200_KERNEL_STREAM && !A->ntiles) return set_error(B200_ERR_STATE, "stream kernel not applicable: a row exceeds the stage capacity");
   if (kernel == B200_KERNEL_CPROW && !A->cprow_use) return set_error(B200_ERR_STATE, "matrix has no compressed-row index");
-  if (kernel == B200_KERNEL_MERGE) return set_error(B200_ERR_STATE, "merge kernel not built for this matrix");
+  if (kernel == B200_KERNEL_MERGE && !A->nmtiles) {
+    std::vector<int32_t> ai((size_t)A->m + 1);
+    B200_CUDA_TRY(cudaMemcpy(ai.data(), A->d_ai, ai.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    B200_TRY(build_merge_plan(A, ai.data()));
+    if (!A->nmtiles) return set_error(B200_ERR_STATE, "merge kernel not applicable (empty matrix)");
+  }
   A->kernel_override = kernel;
   return B200_OK;
 }
@@ -800,6 +941,12 @@ static int spmv_dispatch(b200_csr_s *A, const double *x, const double *yin, doub
   if (mode != B200_MODE_FAST && (kernel == B200_KERNEL_VECTOR || kernel == B200_KERNEL_MERGE))
     return set_error(B200_ERR_ARG, "kernel %d cannot honour an EXACT summation order", kernel);
   if (kernel == B200_KERNEL_VECTOR) return launch_vector<ADD>(A, x, yin, y, st);
+  if (kernel == B200_KERNEL_MERGE) {
+    B200_LAUNCH((k_merge<ADD>), A->nmtiles, MERGE_THREADS, 0, st, A->d_mtiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->d_mhead, A->d_mtail);
+    if (A->nmsplit)
+      B200_LAUNCH((k_merge_fixup<ADD>), (A->nmsplit + 127) / 128, 128, 0, st, A->nmsplit, A->d_msplit, A->d_mhead, A->d_mtail, yin, y);
+    return B200_OK;
+  }
   if (mode == B200_MODE_EXACT) return launch_mode<B200_MODE_EXACT, ADD>(A, kernel, x, yin, y, st);
   return launch_mode<B200_MODE_EXACT_FMA, ADD>(A, kernel, x, yin, y, st);
 }

@@ -50,6 +50,13 @@ def _cases():
     cases["random_ragged"] = (ai, aj, aa, 700)
     ai, aj, aa = gen.random_csr(5000, 300, 3, rng, empty_frac=0.9)
     cases["mostly_empty"] = (ai, aj, aa, 300)
+    # long rows: several times the merge tile capacity (2048), neighbours of every length
+    lens = np.array([1, 0, 5000, 3, 2048, 2049, 0, 0, 7, 4096, 1, 10000, 2, 2047, 300] * 3)
+    ai = np.zeros(len(lens) + 1, np.int32)
+    np.cumsum(lens, out=ai[1:])
+    ncol = 12000
+    aj = np.concatenate([np.sort(rng.choice(ncol, size=l, replace=False)) for l in lens]).astype(np.int32)
+    cases["long_rows"] = (ai, aj, rng.uniform(-1, 1, size=len(aj)), ncol)
     cases["single_row"] = (np.array([0, 3], np.int32), np.array([0, 2, 4], np.int32), np.array([1.5, -2.0, 0.25]), 5)
     cases["all_empty"] = (np.zeros(11, np.int32), np.zeros(0, np.int32), np.zeros(0), 4)
     return cases
@@ -89,9 +96,38 @@ def test_fast_mode_within_row_bound(pk, cuda, name):
     kernels = [None, pk.KERNEL_ROW, pk.KERNEL_VECTOR]
     if info.stream_tiles:
         kernels.append(pk.KERNEL_STREAM)
+    if info.nz:
+        kernels.append(pk.KERNEL_MERGE)
     for k in kernels:
         y = _run(pk, cuda, A, x, pk.MODE_FAST, kernel=k)
         assert np.all(np.abs(y - ref) <= bound), f"{name} kernel={k}: {np.max(np.abs(y - ref) - bound)}"
+    if info.nz:
+        # merge path: deterministic from run to run (no atomics), also for MatMultAdd
+        y1 = _run(pk, cuda, A, x, pk.MODE_FAST, kernel=pk.KERNEL_MERGE)
+        y2 = _run(pk, cuda, A, x, pk.MODE_FAST, kernel=pk.KERNEL_MERGE)
+        assert np.array_equal(y1, y2)
+        y0 = gen.uniform_pm1(len(ai) - 1, seed=11)
+        z = _run(pk, cuda, A, x, pk.MODE_FAST, kernel=pk.KERNEL_MERGE, add=y0)
+        refa = oracle.matmultadd(ai, aj, aa, x, y0)
+        assert np.all(np.abs(z - refa) <= bound + 1e-15 * np.abs(y0))
+    A.destroy()
+
+
+def test_plan_picks_kernel_from_histogram(pk, cuda):
+    p = oracle.poisson7(16)
+    A = pk.Csr(p["ai"], p["aj"], p["aa"])
+    assert pk.KERNEL_NAMES[A.info().kernel_fast] == "stream" and pk.KERNEL_NAMES[A.info().kernel_exact] == "stream"
+    A.destroy()
+    ai, aj, aa = gen.powerlaw(30000, lmax=5000)
+    A = pk.Csr(ai, aj, aa)
+    i = A.info()
+    assert pk.KERNEL_NAMES[i.kernel_fast] == "merge" and i.merge_tiles > 0
+    assert sum(i.hist) == 30000
+    A.destroy()
+    rng = np.random.default_rng(0)
+    ai, aj, aa = gen.random_csr(4000, 100, 2, rng, empty_frac=0.9)
+    A = pk.Csr(ai, aj, aa, n=100)
+    assert pk.KERNEL_NAMES[A.info().kernel_fast] == "cprow"
     A.destroy()
 
 
