@@ -74,6 +74,7 @@ typedef struct {
   int32_t stream_tiles;      /* number of tiles of the STREAM kernel (0 = not applicable)       */
   int32_t merge_tiles;
   int32_t has_transpose;     /* explicit transpose copy is resident                             */
+  int32_t index8_diagonals;  /* > 0: column indices stream as 1-byte codes over this many diagonals */
   int32_t hist[16];          /* row-length histogram: [0],[1],[2],[3-4],[5-8],...,[>16384]      */
   uint64_t device_bytes;     /* HBM held by this handle                                         */
 } b200_csr_info_t;

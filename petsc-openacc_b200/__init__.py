@@ -54,6 +54,7 @@ class CsrInfo(C.Structure):
                 ("kernel_fast", C.c_int32), ("kernel_exact", C.c_int32),
                 ("vector_lanes", C.c_int32), ("stream_tiles", C.c_int32),
                 ("merge_tiles", C.c_int32), ("has_transpose", C.c_int32),
+                ("index8_diagonals", C.c_int32),
                 ("hist", C.c_int32 * 16), ("device_bytes", C.c_uint64)]
 
 

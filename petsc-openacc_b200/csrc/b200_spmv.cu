@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "b200_common.h"
@@ -138,17 +139,32 @@ __global__ void __launch_bounds__(256) k_vector(int m, const int *__restrict__ i
 #define STREAM_PAD 16  // alignment slack (<= 3 + 3) + predicated read-ahead (<= 7)
 #define STREAM_U 8
 
-__host__ __device__ inline size_t stream_stage_bytes(int threads, int cap)
-{
-  return (size_t)(cap + STREAM_PAD) * 12 + (size_t)(threads + 8) * 4;
-}
+// IDX8 (compressed column indices): when a matrix has at most 256 distinct diagonals (col - row),
+// as every stencil matrix on a structured grid has, the kernel streams one byte per non-zero (a
+// code into a table of offsets held in shared memory) instead of the 4-byte column index.  Same
+// values, same order, same bits in y; 9 instead of 12 bytes of DRAM traffic per non-zero.
+#define STREAM_PAD8 48  // byte codes: 16-byte alignment slack on both ends + read-ahead
+struct Idx8Args {
+  const unsigned char *aj8;   // nz (+ pad) codes
+  const int           *offs;  // 256 entries: col = row + offs[code]
+};
 
-template <int MODE, bool ADD, int THREADS, bool HALO>
+__host__ __device__ inline size_t stream_aj_bytes(int cap, bool idx8)
+{
+  return idx8 ? (size_t)((cap + STREAM_PAD8 + 15) & ~15) : (size_t)(cap + STREAM_PAD) * 4;
+}
+__host__ __device__ inline size_t stream_stage_bytes(int threads, int cap, bool idx8 = false)
+{
+  return (size_t)(cap + STREAM_PAD) * 8 + stream_aj_bytes(cap, idx8) + (size_t)(threads + 8) * 4;
+}
+__host__ __device__ inline size_t stream_header_bytes(bool idx8) { return idx8 ? 128 + 1024 : 128; }
+
+template <int MODE, bool ADD, int THREADS, bool HALO, bool IDX8>
 __global__ void __launch_bounds__(THREADS + 32)
     k_stream(const int4 *__restrict__ tiles, int ntiles, const int *__restrict__ ii,
              const int *__restrict__ aj, const double *__restrict__ aa,
              const double *__restrict__ x, const double *yin, double *y, int cap, int stages,
-             const HaloArgs h)
+             const HaloArgs h, const Idx8Args ix)
 {
   // HALO (MatMult_MPIAIJ in one launch): the first h.npush CTAs start with the VecScatterBegin --
   // they push this rank's boundary values into the peers' lvec over NVLink -- and then stream
@@ -161,10 +177,13 @@ __global__ void __launch_bounds__(THREADS + 32)
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full  = reinterpret_cast<uint64_t *>(smem);
   uint64_t *empty = full + stages;
-  unsigned char *stage0 = smem + 128;  // barriers live in the first 128 bytes (stages <= 8)
-  const size_t   sbytes = stream_stage_bytes(THREADS, cap);
+  int           *soffs  = reinterpret_cast<int *>(smem + 128);  // IDX8: the diagonal table
+  unsigned char *stage0 = smem + stream_header_bytes(IDX8);     // barriers live in the first 128 bytes
+  const size_t   sbytes = stream_stage_bytes(THREADS, cap, IDX8);
+  const size_t   aabytes = (size_t)(cap + STREAM_PAD) * 8, ajbytes = stream_aj_bytes(cap, IDX8);
 
   const int tid = threadIdx.x;
+  if (IDX8 && tid < 256) soffs[tid] = __ldg(ix.offs + tid);
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
@@ -189,12 +208,15 @@ __global__ void __launch_bounds__(THREADS + 32)
         const int  nr  = ((d.y + 1 + 3) & ~3) - r0a;
         unsigned char *st  = stage0 + (size_t)s * sbytes;
         double        *saa = reinterpret_cast<double *>(st);
-        int           *saj = reinterpret_cast<int *>(st + (size_t)(cap + STREAM_PAD) * 8);
-        int           *sii = saj + (cap + STREAM_PAD);
-        mbar_expect_tx(&full[s], (uint32_t)(nn * 12 + nr * 4));
+        unsigned char *saj = st + aabytes;
+        int           *sii = reinterpret_cast<int *>(st + aabytes + ajbytes);
+        const int      s16 = d.z & ~15;
+        const int      nn8 = ((d.w + 15) & ~15) - s16;   // IDX8: bytes of codes
+        mbar_expect_tx(&full[s], (uint32_t)(nn * 8 + (IDX8 ? nn8 : nn * 4) + nr * 4));
         if (nn > 0) {
           bulk_g2s(saa, aa + s4, (uint32_t)nn * 8, &full[s], pol);
-          bulk_g2s(saj, aj + s4, (uint32_t)nn * 4, &full[s], pol);
+          if (IDX8) bulk_g2s(saj, ix.aj8 + s16, (uint32_t)nn8, &full[s], pol);
+          else bulk_g2s(saj, aj + s4, (uint32_t)nn * 4, &full[s], pol);
         }
         bulk_g2s(sii, ii + r0a, (uint32_t)nr * 4, &full[s], pol);
       }
@@ -209,8 +231,9 @@ __global__ void __launch_bounds__(THREADS + 32)
     const int4 d = __ldg(tiles + tile);
     unsigned char *st  = stage0 + (size_t)s * sbytes;
     const double  *saa = reinterpret_cast<const double *>(st);
-    const int     *saj = reinterpret_cast<const int *>(st + (size_t)(cap + STREAM_PAD) * 8);
-    const int     *sii = saj + (cap + STREAM_PAD) + (d.x & 3);
+    const int     *saj = reinterpret_cast<const int *>(st + aabytes);
+    const unsigned char *saj8 = st + aabytes;
+    const int     *sii = reinterpret_cast<const int *>(st + aabytes + ajbytes) + (d.x & 3);
     const int      r   = d.x + tid;
     double sum = 0.0;
     if (ADD) { if (r < d.y) sum = yin[r]; }
@@ -218,6 +241,7 @@ __global__ void __launch_bounds__(THREADS + 32)
     if (r < d.y) {
       const int lo = sii[tid], hi = sii[tid + 1];
       const int p  = lo - (d.z & ~3);
+      const int p8 = lo - (d.z & ~15);
       const int n  = hi - lo;
       for (int k = 0; k < n; k += STREAM_U) {
         double av[STREAM_U], xv[STREAM_U];
@@ -225,7 +249,7 @@ __global__ void __launch_bounds__(THREADS + 32)
         for (int j = 0; j < STREAM_U; ++j) {
           const bool ok = (k + j) < n;
           av[j] = saa[p + k + j];
-          int c = saj[p + k + j];
+          const int c = IDX8 ? r + soffs[saj8[p8 + k + j]] : saj[p + k + j];
           xv[j] = ok ? __ldg(x + c) : 0.0;
         }
 #pragma unroll
@@ -288,8 +312,27 @@ __global__ void __launch_bounds__(MERGE_THREADS)
   const int  tid = threadIdx.x, nr = d.y - d.x, s = d.z, e = d.w;
   for (int j = tid; j <= nr; j += MERGE_THREADS) rp[j] = min(max(__ldg(ii + d.x + j), s), e) - s;
   const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-  for (int k = tid; k < e - s; k += MERGE_THREADS)
-    prod[k] = ldg_f64_stream_policy(aa + s + k, pol_stream) * ldg_f64_policy(x + ldg_s32_stream_policy(aj + s + k, pol_stream), pol_keep);
+  {
+    // 8 non-zeros per thread, all index loads first, then all gathers: 8 independent requests in
+    // flight per thread (the gather is the latency-bound part)
+    constexpr int PER = MERGE_CAP / MERGE_THREADS;
+    const int     n   = e - s;
+    int           c[PER];
+    double        a[PER], xv[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int k = tid + i * MERGE_THREADS;
+      c[i] = (k < n) ? ldg_s32_stream_policy(aj + s + k, pol_stream) : 0;
+      a[i] = (k < n) ? ldg_f64_stream_policy(aa + s + k, pol_stream) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) xv[i] = (tid + i * MERGE_THREADS < n) ? ldg_f64_policy(x + c[i], pol_keep) : 0.0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int k = tid + i * MERGE_THREADS;
+      if (k < n) prod[k] = a[i] * xv[i];
+    }
+  }
   __syncthreads();
   int L = 1;
   while (L < 32 && L * nr * 2 <= MERGE_THREADS) L <<= 1;   // lanes per row, uniform over the CTA
@@ -387,6 +430,11 @@ struct b200_csr_s {
   int    *d_cpi = nullptr, *d_ridx = nullptr;
   // stream plan
   int4   *d_tiles = nullptr;
+  // compressed column indices (see IDX8)
+  bool           idx8 = false;
+  unsigned char *d_aj8 = nullptr;
+  int           *d_offs = nullptr;
+  int32_t        noffs = 0;
   std::vector<int4> h_tiles;
   int32_t ntiles = 0, stream_threads = 256, stream_cap = 0, stream_stages = 0, stream_grid = 0;
   size_t  stream_smem = 0;
@@ -431,7 +479,7 @@ static int dev_alloc(T **p, size_t count, b200_csr_s *A)
 template <int THREADS>
 static int stream_occupancy(size_t smem, int *ctas)
 {
-  auto kern = k_stream<B200_MODE_EXACT_FMA, false, THREADS, false>;  // any instantiation: same footprint
+  auto kern = k_stream<B200_MODE_EXACT_FMA, false, THREADS, false, false>;  // any instantiation: same footprint
   B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, kern, THREADS + 32, smem));
   return B200_OK;
 }
@@ -439,11 +487,16 @@ static int stream_occupancy(size_t smem, int *ctas)
 template <int MODE, bool ADD, int THREADS>
 static int stream_set_attr(size_t smem)
 {
-  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, ADD, THREADS, false>,
+  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, ADD, THREADS, false, false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (!ADD)
-    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, false, THREADS, true>,
+  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, ADD, THREADS, false, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!ADD) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, false, THREADS, true, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, false, THREADS, true, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   return B200_OK;
 }
 
@@ -513,8 +566,71 @@ static int build_merge_plan(b200_csr_s *A, const int32_t *ai)
   return B200_OK;
 }
 
+// Compressed column indices: find the distinct diagonals (col - row); with at most 256 of them
+// every column index becomes a one-byte code (see IDX8 at k_stream).  Host work, once per matrix,
+// row blocks in parallel.
+static int build_idx8(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
+{
+  A->idx8 = false;
+  if (!aj || A->nz == 0 || !env_int("B200_INDEX8", 1)) return B200_OK;
+  const int m  = A->m;
+  const int nt = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  auto rows_of = [&](int t) { return std::make_pair((int)((long long)m * t / nt), (int)((long long)m * (t + 1) / nt)); };
+  std::vector<std::vector<int>> local(nt);
+  std::atomic<bool> too_many{false};
+  auto scan = [&](int t) {
+    std::vector<int> &set = local[t];
+    int last = INT32_MIN;
+    const auto [r0, r1] = rows_of(t);
+    for (int r = r0; r < r1 && !too_many.load(std::memory_order_relaxed); ++r)
+      for (int k = ai[r]; k < ai[r + 1]; ++k) {
+        const int d = aj[k] - r;
+        if (d == last) continue;
+        last = d;
+        auto it = std::lower_bound(set.begin(), set.end(), d);
+        if (it == set.end() || *it != d) {
+          set.insert(it, d);
+          if (set.size() > 256) { too_many = true; return; }
+        }
+      }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(scan, t);
+    scan(0);
+    for (auto &x : th) x.join();
+  }
+  if (too_many) return B200_OK;
+  std::vector<int> offs;
+  for (auto &v : local) offs.insert(offs.end(), v.begin(), v.end());
+  std::sort(offs.begin(), offs.end());
+  offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+  if (offs.size() > 256) return B200_OK;
+  std::vector<unsigned char> codes((size_t)A->nz + 64, 0);
+  auto encode = [&](int t) {
+    const auto [r0, r1] = rows_of(t);
+    for (int r = r0; r < r1; ++r)
+      for (int k = ai[r]; k < ai[r + 1]; ++k)
+        codes[k] = (unsigned char)(std::lower_bound(offs.begin(), offs.end(), aj[k] - r) - offs.begin());
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(encode, t);
+    encode(0);
+    for (auto &x : th) x.join();
+  }
+  A->noffs = (int)offs.size();
+  offs.resize(256, 0);
+  B200_TRY(dev_alloc(&A->d_aj8, codes.size(), A));
+  B200_TRY(dev_alloc(&A->d_offs, offs.size(), A));
+  B200_CUDA_TRY(cudaMemcpy(A->d_aj8, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+  B200_CUDA_TRY(cudaMemcpy(A->d_offs, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice));
+  A->idx8 = true;
+  return B200_OK;
+}
+
 // Build the plan from the host row-pointer array.
-static int build_plan(b200_csr_s *A, const int32_t *ai)
+static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
 {
   const int m = A->m;
   // --- statistics ---------------------------------------------------------------------------
@@ -554,6 +670,8 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
   // the 2-deep ring once 1024 are reached (7-point: 256 x 2 stages x 4 CTAs; 27-point: 128 x 1
   // stage x 5 CTAs).  B200_STREAM_* environment variables override for sweeps.
   B200_TRY(stream_set_all_attrs(0, 0));  // opt in to > 48 KB before asking for occupancy
+  if (A->rmax <= 8192) B200_TRY(build_idx8(A, ai, aj));
+  const bool i8 = A->idx8;
   int threads = env_int("B200_STREAM_THREADS", 0), stages = env_int("B200_STREAM_STAGES", 0);
   int cap = env_int("B200_STREAM_CAP", 0);
   auto cap_for = [&](int T) { return std::max(((std::min((int)(T * std::max(mean, 1.0) * 1.05) + 32, 8192) + 3) & ~3), 64); };
@@ -564,7 +682,7 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
       if (threads == 128 || threads == 256) { if (T != threads) continue; }
       for (int S : {2, 1}) {
         if (stages > 0 && S != stages) continue;
-        const size_t smem = 128 + (size_t)S * stream_stage_bytes(T, cap > 0 ? ((cap + 3) & ~3) : cap_for(T));
+        const size_t smem = stream_header_bytes(i8) + (size_t)S * stream_stage_bytes(T, cap > 0 ? ((cap + 3) & ~3) : cap_for(T), i8);
         if (smem > 227 * 1024) continue;
         int ctas = 0;
         if (T == 256) B200_TRY(stream_occupancy<256>(smem, &ctas)); else B200_TRY(stream_occupancy<128>(smem, &ctas));
@@ -594,10 +712,10 @@ static int build_plan(b200_csr_s *A, const int32_t *ai)
       r = r1;
     }
     if (stream_ok) {
-      const size_t sbytes = stream_stage_bytes(threads, cap);
+      const size_t sbytes = stream_stage_bytes(threads, cap, i8);
       stages = std::min(std::max(stages, 1), 8);
-      A->stream_smem = 128 + (size_t)stages * sbytes;
-      if (A->stream_smem > 227 * 1024) { stages = 1; A->stream_smem = 128 + sbytes; }
+      A->stream_smem = stream_header_bytes(i8) + (size_t)stages * sbytes;
+      if (A->stream_smem > 227 * 1024) { stages = 1; A->stream_smem = stream_header_bytes(i8) + sbytes; }
       if (A->stream_smem > 227 * 1024) stream_ok = false;
     }
     if (stream_ok) {
@@ -670,9 +788,9 @@ static void build_host_blocks(b200_csr_s *A, const int32_t *ai, const int32_t *a
   }
 }
 
-static int create_common(b200_csr_s *A, const int32_t *h_ai)
+static int create_common(b200_csr_s *A, const int32_t *h_ai, const int32_t *h_aj)
 {
-  return build_plan(A, h_ai);
+  return build_plan(A, h_ai, h_aj);
 }
 
 extern "C" int b200_init(int device)
@@ -731,7 +849,7 @@ extern "C" int b200_csr_create(b200_csr_t *out, int32_t m, int32_t n, const int3
       B200_CUDA_TRY(cudaMemcpy(A->d_aj, h_aj, (size_t)nz * sizeof(int), cudaMemcpyHostToDevice));
       B200_CUDA_TRY(cudaMemcpy(A->d_aa, h_aa, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice));
     }
-    B200_TRY(create_common(A, h_ai));
+    B200_TRY(create_common(A, h_ai, h_aj));
     if (A->ntiles) build_host_blocks(A, h_ai, h_aj, A->h_tiles);
     return B200_OK;
   }();
@@ -760,7 +878,7 @@ extern "C" int b200_csr_create_from_device(b200_csr_t *out, int32_t m, int32_t n
       B200_CUDA_TRY(cudaMemcpy(A->d_aj, d_aj, (size_t)nz * sizeof(int), cudaMemcpyDeviceToDevice));
       B200_CUDA_TRY(cudaMemcpy(A->d_aa, d_aa, (size_t)nz * sizeof(double), cudaMemcpyDeviceToDevice));
     }
-    return create_common(A, h_ai.data());
+    return create_common(A, h_ai.data(), nullptr);
   }();
   if (rc) { b200_csr_destroy(A); return rc; }
   *out = A;
@@ -781,6 +899,7 @@ extern "C" int b200_csr_destroy(b200_csr_t A)
   if (A->T) b200_csr_destroy(A->T);
   cudaFree(A->d_ai); cudaFree(A->d_aj); cudaFree(A->d_aa);
   cudaFree(A->d_cpi); cudaFree(A->d_ridx); cudaFree(A->d_tiles);
+  cudaFree(A->d_aj8); cudaFree(A->d_offs);
   cudaFree(A->d_mtiles); cudaFree(A->d_msplit); cudaFree(A->d_mhead); cudaFree(A->d_mtail);
   cudaFree(A->d_hx); cudaFree(A->d_hy);
   for (auto &s : A->hs) if (s) cudaStreamDestroy(s);
@@ -801,6 +920,7 @@ extern "C" int b200_csr_get_info(b200_csr_t A, b200_csr_info_t *info)
   info->kernel_fast = A->kernel_fast; info->kernel_exact = A->kernel_exact;
   info->vector_lanes = A->vector_lanes; info->stream_tiles = A->ntiles;
   info->merge_tiles = A->nmtiles; info->has_transpose = A->T != nullptr;
+  info->index8_diagonals = A->idx8 ? A->noffs : 0;
   memcpy(info->hist, A->hist, sizeof A->hist);
   info->device_bytes = A->device_bytes + (A->T ? A->T->device_bytes : 0);
   return B200_OK;
@@ -834,48 +954,42 @@ extern "C" int b200_csr_device_arrays(b200_csr_t A, const int32_t **d_ai, const 
 // ---------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------
+// one place that instantiates the stream kernel for (threads per CTA, halo, index width)
+template <int MODE, bool ADD, bool HALO>
+static int launch_stream_any(b200_csr_s *A, int grid, const int4 *tiles, int ntiles, const double *x,
+                             const double *yin, double *y, const HaloArgs &h, cudaStream_t st)
+{
+  const Idx8Args ix{A->d_aj8, A->d_offs};
+#define B200_STREAM_GO(T, I8)                                                                       \
+  B200_LAUNCH((k_stream<MODE, ADD, T, HALO, I8>), grid, T + 32, A->stream_smem, st, tiles, ntiles, \
+              A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, h, ix)
+  if (A->idx8) { if (A->stream_threads == 256) B200_STREAM_GO(256, true); else B200_STREAM_GO(128, true); }
+  else { if (A->stream_threads == 256) B200_STREAM_GO(256, false); else B200_STREAM_GO(128, false); }
+#undef B200_STREAM_GO
+  return B200_OK;
+}
+
 template <int MODE, bool ADD>
 static int launch_stream(b200_csr_s *A, const double *x, const double *yin, double *y, cudaStream_t st)
 {
-  const HaloArgs none{};
-  if (A->stream_threads == 256)
-    B200_LAUNCH((k_stream<MODE, ADD, 256, false>), A->stream_grid, 256 + 32, A->stream_smem, st, A->d_tiles,
-                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, none);
-  else
-    B200_LAUNCH((k_stream<MODE, ADD, 128, false>), A->stream_grid, 128 + 32, A->stream_smem, st, A->d_tiles,
-                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, none);
-  return B200_OK;
+  return launch_stream_any<MODE, ADD, false>(A, A->stream_grid, A->d_tiles, A->ntiles, x, yin, y, HaloArgs{}, st);
 }
 
 // tiles [t0, t0 + nt) only: the row-blocked host pipeline
 template <int MODE, bool ADD>
 static int launch_stream_range(b200_csr_s *A, int t0, int nt, const double *x, const double *yin, double *y, cudaStream_t st)
 {
-  const HaloArgs none{};
-  const int grid = std::min(nt, A->stream_grid);
-  if (A->stream_threads == 256)
-    B200_LAUNCH((k_stream<MODE, ADD, 256, false>), grid, 256 + 32, A->stream_smem, st, A->d_tiles + t0,
-                nt, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, none);
-  else
-    B200_LAUNCH((k_stream<MODE, ADD, 128, false>), grid, 128 + 32, A->stream_smem, st, A->d_tiles + t0,
-                nt, A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, none);
-  return B200_OK;
+  return launch_stream_any<MODE, ADD, false>(A, std::min(nt, A->stream_grid), A->d_tiles + t0, nt, x, yin, y, HaloArgs{}, st);
 }
 
-// MatMult_MPIAIJ in one launch (see k_stream, HALO): push CTAs first in the grid, then the
-// persistent stream CTAs.
+// MatMult_MPIAIJ in one launch (see k_stream, HALO): push prologue on the first CTAs, then the
+// persistent stream loop, then the ghost rows.
 template <int MODE>
 static int launch_stream_halo_mode(b200_csr_s *A, const double *x, double *y, const HaloArgs &h, cudaStream_t st)
 {
   const int grid = A->stream_grid;  // cta_ptr/cta_rows were built for exactly this grid
   if (h.npush > grid) return set_error(B200_ERR_STATE, "more push blocks (%d) than CTAs (%d)", h.npush, grid);
-  if (A->stream_threads == 256)
-    B200_LAUNCH((k_stream<MODE, false, 256, true>), grid, 256 + 32, A->stream_smem, st, A->d_tiles,
-                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, nullptr, y, A->stream_cap, A->stream_stages, h);
-  else
-    B200_LAUNCH((k_stream<MODE, false, 128, true>), grid, 128 + 32, A->stream_smem, st, A->d_tiles,
-                A->ntiles, A->d_ai, A->d_aj, A->d_aa, x, nullptr, y, A->stream_cap, A->stream_stages, h);
-  return B200_OK;
+  return launch_stream_any<MODE, false, true>(A, grid, A->d_tiles, A->ntiles, x, nullptr, y, h, st);
 }
 
 namespace b200 {

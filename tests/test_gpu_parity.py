@@ -263,3 +263,31 @@ def test_host_vector_pipeline_blocks(pk, cuda, monkeypatch, case):
     assert np.array_equal(y1, oracle.matmult(ai, aj, aa, x))
     hx.free(); hy.free()
     A.destroy()
+
+
+def test_compressed_index_plan_and_equivalence(pk, cuda, monkeypatch):
+    """Stencil matrices stream 1-byte diagonal codes; results are the same bits as with int32
+    column indices, and matrices with more than 256 diagonals keep int32."""
+    p = oracle.poisson7(20)
+    x = gen.uniform_pm1(8000, 3)
+    ref = oracle.matmult(p["ai"], p["aj"], p["aa"], x)
+    A8 = pk.Csr(p["ai"], p["aj"], p["aa"])
+    assert A8.info().index8_diagonals == 7
+    y8 = _run(pk, cuda, A8, x, pk.MODE_EXACT, kernel=pk.KERNEL_STREAM)
+    monkeypatch.setenv("B200_INDEX8", "0")
+    A32 = pk.Csr(p["ai"], p["aj"], p["aa"])
+    assert A32.info().index8_diagonals == 0
+    y32 = _run(pk, cuda, A32, x, pk.MODE_EXACT, kernel=pk.KERNEL_STREAM)
+    assert np.array_equal(y8, ref) and np.array_equal(y32, ref)
+    monkeypatch.delenv("B200_INDEX8")
+    ai, aj, aa = gen.stencil27(12, seed=1)
+    A = pk.Csr(ai, aj, aa)
+    assert A.info().index8_diagonals == 27
+    A.destroy()
+    rng = np.random.default_rng(1)
+    ai, aj, aa = gen.random_csr(3000, 3000, 8, rng)
+    A = pk.Csr(ai, aj, aa)
+    assert A.info().index8_diagonals == 0     # thousands of distinct diagonals
+    xr = gen.uniform_pm1(3000, 4)
+    assert np.array_equal(_run(pk, cuda, A, xr, pk.MODE_EXACT), oracle.matmult(ai, aj, aa, xr))
+    A.destroy(); A8.destroy(); A32.destroy()
