@@ -73,7 +73,7 @@ struct HaloArgs {
   unsigned long long  timeout_ns;
 };
 // internal (not part of the C ABI): the stream plan of a matrix and the fused launch
-int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid);   // 0 tiles = not applicable
+int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid, int *threads);   // 0 tiles = not applicable
 int launch_stream_halo(b200_csr_t A, const double *x, double *y, int mode, const HaloArgs &h,
                        cudaStream_t st);
 
@@ -116,15 +116,26 @@ __device__ __forceinline__ void halo_push_block(const HaloArgs &h, const double 
     }
   }
 }
-// acquire every source rank's flag (>= seq), bounded by the spin budget
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Wait until every source rank's flag is >= seq, bounded by the spin budget.  RELAXED system-scope
+// loads and NO system fence: the ghost values are read with ld.global.cg (L2 only, never L1), the
+// peer's stores reach this GPU's L2 in release order (data before flag), so once the flag is seen
+// in L2 the data is there too.  An acquire at system scope would make ptxas emit an L1 invalidation
+// (CCTL.IVALL) and, measured on B200, a system-scope fence executed by every resident CTA costs
+// tens of microseconds per MatMult; keep such fences to the release side, one per SM.
 __device__ __forceinline__ void halo_wait_flags(const HaloArgs &h)
 {
   const unsigned long long t0 = globaltimer_ns();
   for (int s = 0; s < h.nsrc; ++s) {
     const unsigned long long *f = h.flags + h.srcs[s];
-    while (ld_acquire_sys(f) < h.seq) {
+    while (ld_relaxed_sys(f) < h.seq) {
       if (globaltimer_ns() - t0 > h.timeout_ns) { atomicExch(h.err, 1ull); break; }
-      __nanosleep(64);
+      __nanosleep(100);
     }
   }
 }

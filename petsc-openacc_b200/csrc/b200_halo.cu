@@ -278,8 +278,8 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
   // (tile t belongs to CTA t % grid), so that each CTA finishes exactly the rows it wrote
   {
     int4 *d_tiles = nullptr;
-    int   ntiles = 0, grid = 0;
-    B200_TRY(stream_plan_tiles(M->A, &d_tiles, &ntiles, &grid));
+    int   ntiles = 0, grid = 0, threads = 0;
+    B200_TRY(stream_plan_tiles(M->A, &d_tiles, &ntiles, &grid, &threads));
     if (ntiles && grid > 0 && env_int("B200_MPIAIJ_FUSED", 1)) {
       std::vector<int4> tiles((size_t)ntiles);
       B200_CUDA_TRY(cudaMemcpy(tiles.data(), d_tiles, sizeof(int4) * (size_t)ntiles, cudaMemcpyDeviceToHost));
@@ -359,6 +359,15 @@ static int prepare_push(b200_mpiaij_s *M)
   std::vector<PushBlock> blocks;
   std::vector<PushPeer>  peers;
   M->send_start.clear();
+  // fused launch: one push block per SM (the first wave places CTA b on SM b), so that each SM
+  // executes a single system-scope release fence; stand-alone push kernel: PUSH_CHUNK per CTA
+  int chunk = PUSH_CHUNK;
+  if (M->fused_ok) {
+    long long total = 0;
+    for (auto &s : M->sends) total += s.count;
+    const int room = std::max(1, std::min(M->fused_grid, sm_count()) - (int)M->sends.size());
+    chunk = (int)std::max<long long>(64, ((total + room - 1) / room + 31) / 32 * 32);
+  }
   int slot = 0;
   for (auto &s : M->sends) {
     if (!s.peer_window) return set_error(B200_ERR_STATE, "peer %d needs data but its window is not mapped", s.peer);
@@ -369,10 +378,10 @@ static int prepare_push(b200_mpiaij_s *M)
     p.dst[0] = (double *)(w + WINDOW_HDR_BYTES) + s.peer_offset - start;
     p.dst[1] = (double *)(w + WINDOW_HDR_BYTES) + s.peer_ngpad + s.peer_offset - start;
     p.flag   = (unsigned long long *)w + M->rank;
-    p.nblocks = (s.count + PUSH_CHUNK - 1) / PUSH_CHUNK;
+    p.nblocks = (s.count + chunk - 1) / chunk;
     p.pad = 0;
     for (int b = 0; b < p.nblocks; ++b)
-      blocks.push_back(PushBlock{slot, start + b * PUSH_CHUNK, std::min(PUSH_CHUNK, s.count - b * PUSH_CHUNK), 0});
+      blocks.push_back(PushBlock{slot, start + b * chunk, std::min(chunk, s.count - b * chunk), 0});
     M->send_start.push_back(start);
     flat.insert(flat.end(), s.idx.begin(), s.idx.end());
     peers.push_back(p);

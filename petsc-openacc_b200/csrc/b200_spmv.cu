@@ -160,20 +160,26 @@ __host__ __device__ inline size_t stream_stage_bytes(int threads, int cap, bool 
 __host__ __device__ inline size_t stream_header_bytes(bool idx8) { return idx8 ? 128 + 1024 : 128; }
 
 template <int MODE, bool ADD, int THREADS, bool HALO, bool IDX8>
-__global__ void __launch_bounds__(THREADS + 32)
+__global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     k_stream(const int4 *__restrict__ tiles, int ntiles, const int *__restrict__ ii,
              const int *__restrict__ aj, const double *__restrict__ aa,
              const double *__restrict__ x, const double *yin, double *y, int cap, int stages,
              const HaloArgs h, const Idx8Args ix)
 {
-  // HALO (MatMult_MPIAIJ in one launch): the first h.npush CTAs start with the VecScatterBegin --
-  // they push this rank's boundary values into the peers' lvec over NVLink -- and then stream
-  // tiles like every other CTA.  After its last tile a CTA acquires the peers' flags (by then the
-  // ghost values have long arrived: the wait is off the critical path) and adds B*lvec to the
-  // ghost-touching rows of the tiles it owns.
-  if (HALO && (int)blockIdx.x < h.npush) halo_push_block(h, x, blockIdx.x);
+  // HALO = MatMult_MPIAIJ in one launch:
+  //  * VecScatterBegin: the first h.npush CTAs (at most one per SM) start by storing a block of this
+  //    rank's boundary values into a peer's lvec over NVLink and, once a peer's last block is out,
+  //    releasing that peer's flag; then they stream tiles like every other CTA;
+  //  * VecScatterEnd + MatMultAdd(B, lvec, y, y): after its last tile a CTA waits for the flags of
+  //    this rank's sources (the ghosts arrived long ago: the wait is off the critical path) and
+  //    continues the rows of its own tiles that touch a ghost -- A terms first, then B terms, the
+  //    order of MatMult followed by MatMultAdd.
+  // Measured alternatives (profiles/r01_fused_halo_notes.md): folding the ghost terms into the tile
+  // loop behind a per-tile bit mask, a separate communication warp, spreading the push over every
+  // CTA -- all slower than this arrangement.
   const int bid = (int)blockIdx.x;
   const int nb  = (int)gridDim.x;
+  if (HALO && bid < h.npush) halo_push_block(h, x, bid);
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full  = reinterpret_cast<uint64_t *>(smem);
   uint64_t *empty = full + stages;
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(THREADS + 32)
           const bool ok = (k + j) < n;
           av[j] = saa[p + k + j];
           const int c = IDX8 ? r + soffs[saj8[p8 + k + j]] : saj[p + k + j];
-          xv[j] = ok ? __ldg(x + c) : 0.0;
+          xv[j] = __ldg(x + (ok ? c : 0));   // unconditional load (x[0] past the row end): keeps the 8 gathers batched
         }
 #pragma unroll
         for (int j = 0; j < STREAM_U; ++j)
@@ -262,13 +268,12 @@ __global__ void __launch_bounds__(THREADS + 32)
     if ((tid & 31) == 0) mbar_arrive(&empty[s]);
   }
   if (HALO) {
-    // VecScatterEnd + MatMultAdd(B, lvec, y, y) for the tiles of this CTA.  One lane per source
-    // rank acquires that rank's flag; the consumer-only barrier publishes the flags and this
-    // CTA's y stores.  cta_rows lists the ghost-touching rows of the tiles this CTA owns.
+    // one lane per source rank waits for that rank's flag; the consumer-only barrier publishes the
+    // flags and this CTA's y stores; cta_rows lists the ghost-touching rows of this CTA's tiles
     if (tid < h.nsrc) {
       const unsigned long long t0 = globaltimer_ns();
       const unsigned long long *f = h.flags + h.srcs[tid];
-      while (ld_acquire_sys(f) < h.seq) {
+      while (ld_relaxed_sys(f) < h.seq) {
         if (globaltimer_ns() - t0 > h.timeout_ns) { atomicExch(h.err, 1ull); break; }
         __nanosleep(32);
       }
@@ -713,7 +718,7 @@ static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
     }
     if (stream_ok) {
       const size_t sbytes = stream_stage_bytes(threads, cap, i8);
-      stages = std::min(std::max(stages, 1), 8);
+      stages = std::min(std::max(stages, 1), 7);  // 2 x 7 mbarriers + the halo arrival word fit the 128-byte header
       A->stream_smem = stream_header_bytes(i8) + (size_t)stages * sbytes;
       if (A->stream_smem > 227 * 1024) { stages = 1; A->stream_smem = stream_header_bytes(i8) + sbytes; }
       if (A->stream_smem > 227 * 1024) stream_ok = false;
@@ -987,16 +992,17 @@ static int launch_stream_range(b200_csr_s *A, int t0, int nt, const double *x, c
 template <int MODE>
 static int launch_stream_halo_mode(b200_csr_s *A, const double *x, double *y, const HaloArgs &h, cudaStream_t st)
 {
-  const int grid = A->stream_grid;  // cta_ptr/cta_rows were built for exactly this grid
+  const int grid = A->stream_grid;  // cta_ptr / cta_rows were built for exactly this grid
   if (h.npush > grid) return set_error(B200_ERR_STATE, "more push blocks (%d) than CTAs (%d)", h.npush, grid);
   return launch_stream_any<MODE, false, true>(A, grid, A->d_tiles, A->ntiles, x, nullptr, y, h, st);
 }
 
 namespace b200 {
-int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid)
+int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid, int *threads)
 {
   *d_tiles = A->d_tiles;
   *grid    = A->stream_grid;
+  *threads = A->stream_threads;
   *ntiles  = A->kernel_override && A->kernel_override != B200_KERNEL_STREAM ? 0 : A->ntiles;
   return B200_OK;
 }
