@@ -81,6 +81,16 @@ int b200_mpiaij_mult_host(b200_mpiaij_t M, const double *h_x, double *h_y, int m
 int b200_mpiaij_pack(b200_mpiaij_t M, int32_t peer, const double *d_x, double *d_buf, void *stream);
 int b200_mpiaij_mult_add_ghost(b200_mpiaij_t M, const double *d_lvec, double *d_y, int mode,
                                void *stream);
+/* ---- CG on the partitioned matrix (KSPSolve_CG's VecDot/VecNorm need a global sum) ------------ */
+/* The all-reduce needs every rank's window: pass the rank's IPC handle (other process), or its
+ * device pointer (same process), or neither when the halo already mapped it.                   */
+int b200_mpiaij_set_rank_window(b200_mpiaij_t M, int32_t rank, const void *handle64_or_null,
+                                void *d_window_or_null);
+/* in-place sum of 1..3 device scalars over all ranks, added in rank order (same bits everywhere) */
+int b200_mpiaij_allreduce_sum(b200_mpiaij_t M, double *d_vals, int32_t nvals, void *stream);
+/* KSPCG + PCJACOBI; d_b, d_x are this rank's rows; collective over the ranks                   */
+int b200_mpiaij_cg_jacobi(b200_mpiaij_t M, const double *d_b, double *d_x, double rtol, double atol,
+                          int32_t max_it, int mode, b200_cg_result_t *res, void *stream);
 /* non-zero after a flag wait ran out of its spin budget (B200_MPIAIJ_TIMEOUT_MS, default 2000) */
 int b200_mpiaij_check(b200_mpiaij_t M);
 

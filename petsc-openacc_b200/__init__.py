@@ -289,6 +289,7 @@ MPIAIJ_SYMBOLS = [
     "b200_mpiaij_set_peer_window", "b200_mpiaij_mult_begin", "b200_mpiaij_mult_local",
     "b200_mpiaij_mult_end", "b200_mpiaij_mult", "b200_mpiaij_pack", "b200_mpiaij_mult_add_ghost",
     "b200_mpiaij_check", "b200_mpiaij_mult_host", "b200_mpiaij_mult_finish",
+    "b200_mpiaij_set_rank_window", "b200_mpiaij_allreduce_sum", "b200_mpiaij_cg_jacobi",
 ]
 ABI_SYMBOLS += MPIAIJ_SYMBOLS
 
@@ -380,6 +381,19 @@ class MpiAij:
 
     def mult_host(self, hx, hy, mode=MODE_FAST):
         check(lib.b200_mpiaij_mult_host(self._h, _np_ptr(hx), _np_ptr(hy), C.c_int(mode)))
+
+    def set_rank_window(self, q, handle=None, ptr=None):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        check(lib.b200_mpiaij_set_rank_window(self._h, C.c_int32(q), buf, C.c_void_p(ptr or 0)))
+
+    def allreduce_sum(self, vals, stream=None):
+        check(lib.b200_mpiaij_allreduce_sum(self._h, _dptr(vals), C.c_int32(vals.numel()), _stream(stream)))
+
+    def cg_jacobi(self, b, x, rtol=1e-14, atol=1e-12, max_it=10000, mode=MODE_FAST, stream=None):
+        res = CgResult()
+        check(lib.b200_mpiaij_cg_jacobi(self._h, _dptr(b), _dptr(x), C.c_double(rtol), C.c_double(atol),
+                                        C.c_int32(max_it), C.c_int(mode), C.byref(res), _stream(stream)))
+        return res
 
     def pack(self, peer, x, buf, stream=None):
         check(lib.b200_mpiaij_pack(self._h, C.c_int32(peer), _dptr(x), _dptr(buf), _stream(stream)))

@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <functional>
 #include <string>
 
 #include "../../include/b200_seqaij.h"
@@ -72,6 +73,17 @@ struct HaloArgs {
   unsigned long long *err;
   unsigned long long  timeout_ns;
 };
+// the CG body shared by b200_cg_jacobi and b200_mpiaij_cg_jacobi (b200_vec.cu)
+struct CgOps {
+  int            m = 0;                       // local rows
+  const int32_t *ai = nullptr, *aj = nullptr; // diagonal block (for PCJACOBI)
+  const double  *aa = nullptr;
+  std::function<int(const double *, double *, cudaStream_t)> mult;       // w = A p
+  std::function<int(double *, int, cudaStream_t)>            allreduce;  // in place, device scalars; empty on one GPU
+};
+int cg_jacobi_run(const CgOps &ops, const double *d_b, double *d_x, double rtol, double atol,
+                  int32_t max_it, b200_cg_result_t *res, cudaStream_t st);
+
 // internal (not part of the C ABI): the stream plan of a matrix and the fused launch
 int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid, int *threads);   // 0 tiles = not applicable
 int launch_stream_halo(b200_csr_t A, const double *x, double *y, int mode, const HaloArgs &h,

@@ -8,8 +8,9 @@
 // in the peer's window; the peer's off-diagonal kernel acquires the flags and adds B*lvec.
 //
 // Window layout (one cudaMalloc per rank, exported with cudaIpcGetMemHandle):
-//   [0, 1024)                      uint64 flags[size<=120] ; word 126 = error, word 127 = magic
-//   [1024, 1024 + 8*ngpad)         lvec buffer 0
+//   [0, 1024)                      uint64 flags[size<=120] ; word 126 = error
+//   [1024, 8704)                   all-reduce slots red[2][120] = {v0, v1, v2, seq}
+//   [16384, 16384 + 8*ngpad)       lvec buffer 0
 //   [.. + 8*ngpad, .. + 16*ngpad)  lvec buffer 1          (ngpad = nghost rounded up to 16)
 // Buffers alternate with the MatMult sequence number, which makes the exchange safe without a
 // reverse "buffer free" signal: a peer can only be one MatMult ahead of this rank.
@@ -25,7 +26,9 @@ using namespace b200;
 
 namespace {
 
-constexpr int    WINDOW_HDR_BYTES = 1024;
+constexpr int    WINDOW_HDR_BYTES = 16384;  // 1 KB of flags + the all-reduce slots
+constexpr int    RED_SLOT_OFFSET  = 1024;   // red[parity][source rank] = {v0, v1, v2, seq}: 2 x 120 x 32 B
+constexpr int    RED_MAX_VALS     = 3;
 constexpr int    MAX_RANKS        = 120;
 constexpr int    ERR_WORD         = 126;
 constexpr int    PUSH_CHUNK       = 2304;  // elements per CTA of the push role (8 per thread of a 288-thread CTA)
@@ -77,6 +80,40 @@ __global__ void __launch_bounds__(128)
   y[i] = sum;
 }
 
+// All-reduce (sum) of up to 3 device scalars over the ranks, through the same peer windows:
+// rank r stores {values, seq} into slot [seq & 1][r] of EVERY rank's window (its own included),
+// then reads all slots of its own window and adds them in rank order -- every rank gets the same
+// bits.  Slots alternate with the sequence number; a rank can be at most one all-reduce ahead of
+// a peer, so two slots per source are enough.  One CTA, one lane per rank.
+struct RedSlot { double v[3]; unsigned long long seq; };
+__global__ void __launch_bounds__(128)
+    k_allreduce(double *vals, int nvals, int size, int rank, unsigned char *const *windows,
+                unsigned long long seq, unsigned long long *err, unsigned long long timeout_ns)
+{
+  __shared__ double sv[MAX_RANKS][RED_MAX_VALS];
+  const int t = threadIdx.x;
+  if (t < size) {
+    RedSlot *dst = reinterpret_cast<RedSlot *>(windows[t] + RED_SLOT_OFFSET) + (seq & 1) * MAX_RANKS + rank;
+    for (int k = 0; k < nvals; ++k) dst->v[k] = vals[k];
+    __threadfence_system();
+    st_release_sys(&dst->seq, seq);
+    const RedSlot *src = reinterpret_cast<const RedSlot *>(windows[rank] + RED_SLOT_OFFSET) + (seq & 1) * MAX_RANKS + t;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_relaxed_sys(&src->seq) < seq) {
+      if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(err, 1ull); break; }
+      __nanosleep(32);
+    }
+    __threadfence_system();
+    for (int k = 0; k < nvals; ++k) sv[t][k] = __ldcg(&src->v[k]);
+  }
+  __syncthreads();
+  if (t < nvals) {
+    double s = 0.0;
+    for (int q = 0; q < size; ++q) s += sv[q][t];
+    vals[t] = s;
+  }
+}
+
 }  // namespace
 
 struct b200_mpiaij_s {
@@ -107,6 +144,11 @@ struct b200_mpiaij_s {
   cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
   unsigned long long timeout_ns = 2000ull * 1000000ull;
   int *d_cta_ptr = nullptr, *d_cta_rows = nullptr;  // fused launch: B rows grouped by owning CTA
+  // all-reduce: every rank's window (own included), in rank order
+  std::vector<unsigned char *> all_windows;
+  std::vector<char> all_windows_opened;
+  unsigned char **d_all_windows = nullptr;
+  unsigned long long rseq = 0;
   int   fused_grid = 0;
   bool  fused_ok = false;
 };
@@ -174,6 +216,9 @@ extern "C" int b200_mpiaij_destroy(b200_mpiaij_t M)
   if (M->B) b200_csr_destroy(M->B);
   cudaFree(M->d_cpi); cudaFree(M->d_ridx); cudaFree(M->d_bj); cudaFree(M->d_ba); cudaFree(M->d_srcs);
   cudaFree(M->d_cta_ptr); cudaFree(M->d_cta_rows);
+  cudaFree(M->d_all_windows);
+  for (int q = 0; q < (int)M->all_windows.size(); ++q)
+    if (q != M->rank && M->all_windows[q] && M->all_windows_opened[q]) cudaIpcCloseMemHandle(M->all_windows[q]);
   cudaFree(M->d_send_idx); cudaFree(M->d_window); cudaFree(M->d_blocks); cudaFree(M->d_peers); cudaFree(M->d_done);
   if (M->side) cudaStreamDestroy(M->side);
   if (M->hstream) cudaStreamDestroy(M->hstream);
@@ -532,4 +577,59 @@ extern "C" int b200_mpiaij_check(b200_mpiaij_t M)
   B200_CUDA_TRY(cudaMemcpy(&e, (unsigned long long *)M->d_window + ERR_WORD, sizeof e, cudaMemcpyDeviceToHost));
   if (e) return set_error(B200_ERR_TIMEOUT, "rank %d: a halo flag was not seen within the spin budget", M->rank);
   return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// all-reduce and the distributed CG
+// ---------------------------------------------------------------------------------------------
+// Windows of ALL ranks are needed for the all-reduce (the halo only maps the peers it sends to).
+extern "C" int b200_mpiaij_set_rank_window(b200_mpiaij_t M, int32_t q, const void *handle64_or_null, void *d_window_or_null)
+{
+  if (!M || !M->uploaded || q < 0 || q >= M->size) return set_error(B200_ERR_ARG, "b200_mpiaij_set_rank_window: bad argument");
+  if (M->all_windows.empty()) { M->all_windows.assign(M->size, nullptr); M->all_windows_opened.assign(M->size, 0); }
+  if (q == M->rank) { M->all_windows[q] = M->d_window; return B200_OK; }
+  // reuse a mapping the halo already opened
+  for (auto &s : M->sends)
+    if (s.peer == q && s.peer_window) { M->all_windows[q] = (unsigned char *)s.peer_window; return B200_OK; }
+  if (d_window_or_null) { M->all_windows[q] = (unsigned char *)d_window_or_null; return B200_OK; }
+  if (!handle64_or_null) return set_error(B200_ERR_ARG, "no window for rank %d", q);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64_or_null, 64);
+  void *p = nullptr;
+  B200_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  M->all_windows[q] = (unsigned char *)p;
+  M->all_windows_opened[q] = 1;
+  return B200_OK;
+}
+
+extern "C" int b200_mpiaij_allreduce_sum(b200_mpiaij_t M, double *d_vals, int32_t nvals, void *stream)
+{
+  if (!M || !M->uploaded || !d_vals || nvals < 1 || nvals > RED_MAX_VALS) return set_error(B200_ERR_ARG, "b200_mpiaij_allreduce_sum: bad argument");
+  if (M->size == 1) return B200_OK;
+  if (M->all_windows.empty()) return set_error(B200_ERR_STATE, "b200_mpiaij_set_rank_window for every rank first");
+  if (!M->d_all_windows) {
+    M->all_windows[M->rank] = M->d_window;
+    for (int q = 0; q < M->size; ++q)
+      if (!M->all_windows[q]) return set_error(B200_ERR_STATE, "window of rank %d is not mapped", q);
+    B200_TRY(up(&M->d_all_windows, M->all_windows));
+  }
+  M->rseq += 1;
+  B200_LAUNCH(k_allreduce, 1, 128, 0, (cudaStream_t)stream, d_vals, nvals, M->size, M->rank, M->d_all_windows, M->rseq,
+              (unsigned long long *)M->d_window + ERR_WORD, M->timeout_ns);
+  return B200_OK;
+}
+
+// KSPCG + PCJACOBI on the row-partitioned matrix: MatMult_MPIAIJ (one fused launch) + the vector
+// kernels of b200_vec.cu on the local rows + all-reduced dot products.
+extern "C" int b200_mpiaij_cg_jacobi(b200_mpiaij_t M, const double *d_b, double *d_x, double rtol, double atol,
+                                     int32_t max_it, int mode, b200_cg_result_t *res, void *stream)
+{
+  if (!M || !M->uploaded || !d_b || !d_x || !res) return set_error(B200_ERR_ARG, "b200_mpiaij_cg_jacobi: bad argument");
+  CgOps ops;
+  ops.m = M->nloc;
+  B200_TRY(b200_csr_device_arrays(M->A, &ops.ai, &ops.aj, &ops.aa));
+  ops.mult = [M, mode](const double *p, double *w, cudaStream_t s) { return b200_mpiaij_mult(M, p, w, mode, s); };
+  if (M->size > 1) ops.allreduce = [M](double *v, int n, cudaStream_t s) { return b200_mpiaij_allreduce_sum(M, v, n, s); };
+  B200_TRY(cg_jacobi_run(ops, d_b, d_x, rtol, atol, max_it, res, (cudaStream_t)stream));
+  return b200_mpiaij_check(M);
 }

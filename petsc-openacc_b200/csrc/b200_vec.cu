@@ -160,7 +160,7 @@ __global__ void k_pmult(double *__restrict__ w, const double *__restrict__ x, co
 
 // ------------------------------- CG pieces ---------------------------------------------------
 // scalars in device memory: sc[0]=beta sc[1]=betaold sc[2]=dpi sc[3]=dp (norm) sc[4]=beta_new
-enum { S_BETA = 0, S_BETAOLD = 1, S_DPI = 2, S_DP = 3, S_BETANEW = 4, S_COUNT = 8 };
+enum { S_BETA = 0, S_BETAOLD = 1, S_DPI = 2, S_DP = 3, S_BETANEW = 4, S_ZZ = 5, S_ZR = 6, S_COUNT = 8 };  // S_ZZ, S_ZR, S_DPI: raw (all-reducible) sums
 
 // dinv[i] = 1/a_ii (PCJACOBI [P376]: zero diagonal -> 1)
 __global__ void k_diag_inv(int m, const int *__restrict__ ii, const int *__restrict__ aj,
@@ -188,7 +188,14 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_init(long long n, const doub
     zr   = __fma_rn(zi, ri, zr);
   }
   block_reduce2<false>(zz, zr);
-  grid_finish2<false>(zz, zr, partials, counter, sc + S_DP, sc + S_BETA, 1);
+  grid_finish2<false>(zz, zr, partials, counter, sc + S_ZZ, sc + S_ZR, 0);
+}
+
+// after the (all-reduced) sums of k_cg_init: dp = sqrt(zz), beta = (z,r)
+__global__ void k_cg_post_init(double *sc)
+{
+  sc[S_DP]   = sqrt(sc[S_ZZ]);
+  sc[S_BETA] = sc[S_ZR];
 }
 
 // p = z + (beta/betaold) p   (first iteration: p = z);  betaold <- beta happens in k_cg_step
@@ -219,14 +226,16 @@ __global__ void __launch_bounds__(RED_THREADS)
     zr        = __fma_rn(zi, ri, zr);
   }
   block_reduce2<false>(zz, zr);
-  grid_finish2<false>(zz, zr, partials, counter, sc + S_DP, sc + S_BETANEW, 1);
+  grid_finish2<false>(zz, zr, partials, counter, sc + S_ZZ, sc + S_ZR, 0);
 }
 
-// betaold <- beta; beta <- beta_new   (one thread)
+// after the (all-reduced) sums of k_cg_step: dp = sqrt(zz); betaold <- beta; beta <- (z,r)
 __global__ void k_cg_rotate(double *sc)
 {
+  sc[S_DP]      = sqrt(sc[S_ZZ]);
+  sc[S_BETANEW] = sc[S_ZR];
   sc[S_BETAOLD] = sc[S_BETA];
-  sc[S_BETA]    = sc[S_BETANEW];
+  sc[S_BETA]    = sc[S_ZR];
 }
 
 int ew_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)std::max(1, sm_count()) * 16)); }
@@ -298,26 +307,19 @@ extern "C" int b200_vec_sum(const double *d_x, int64_t n, double *d_out, void *s
 }
 
 // ---------------------------------------------------------------------------------------------
-// b200_cg_jacobi: KSPSolve_CG [P376] (left preconditioning, preconditioned-residual norm, zero
-// initial guess, KSPConvergedDefault: rnorm < max(rtol*rnorm0, atol)), PCJACOBI.
-// Per iteration: 1 p-update, 1 SpMV, 1 dot, 1 fused step, 1 rotate, one 8-byte read-back.
+// KSPSolve_CG [P376] (left preconditioning, preconditioned-residual norm, zero initial guess,
+// KSPConvergedDefault: rnorm < max(rtol*rnorm0, atol)), PCJACOBI.  One body for the single-GPU and
+// the row-partitioned solve: `mult` is MatMult, `allreduce` sums device scalars over the ranks
+// (absent on one GPU).  Per iteration: p-update, MatMult, dot, one fused x/r/z/norm/(z,r) kernel,
+// one scalar kernel, one 64-byte read-back.
 // ---------------------------------------------------------------------------------------------
-extern "C" int b200_cg_jacobi(b200_csr_t A, const double *d_b, double *d_x, double rtol,
-                              double atol, int32_t max_it, int mode, b200_cg_result_t *res,
-                              void *stream)
+namespace b200 {
+int cg_jacobi_run(const CgOps &ops, const double *d_b, double *d_x, double rtol, double atol,
+                  int32_t max_it, b200_cg_result_t *res, cudaStream_t st)
 {
-  if (!A || !d_b || !d_x || !res) return set_error(B200_ERR_ARG, "b200_cg_jacobi: null argument");
   B200_TRY(ensure_device());
-  b200_csr_info_t info;
-  B200_TRY(b200_csr_get_info(A, &info));
-  if (info.m != info.n) return set_error(B200_ERR_ARG, "b200_cg_jacobi: matrix must be square");
-  const int          m  = info.m;
-  const long long    n  = m;
-  cudaStream_t       st = (cudaStream_t)stream;
-  const int32_t     *d_ai, *d_aj;
-  const double      *d_aa;
-  B200_TRY(b200_csr_device_arrays(A, &d_ai, &d_aj, &d_aa));
-
+  const int       m = ops.m;
+  const long long n = m;
   double *buf = nullptr, *sc = nullptr, *h_sc = nullptr;
   B200_CUDA_TRY(cudaMalloc((void **)&buf, sizeof(double) * 5 * (size_t)std::max(m, 1)));
   B200_CUDA_TRY(cudaMalloc((void **)&sc, sizeof(double) * S_COUNT));
@@ -333,11 +335,13 @@ extern "C" int b200_cg_jacobi(b200_csr_t A, const double *d_b, double *d_x, doub
     unsigned *counter;
     B200_CUDA_TRY(cudaEventRecord(e0, st));
     B200_CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(double) * S_COUNT, st));
-    if (m) B200_LAUNCH(k_diag_inv, (m + 127) / 128, 128, 0, st, m, d_ai, d_aj, d_aa, dinv);
+    if (m) B200_LAUNCH(k_diag_inv, (m + 127) / 128, 128, 0, st, m, ops.ai, ops.aj, ops.aa, dinv);
     B200_TRY(b200_vec_set(d_x, 0.0, n, st));
     B200_TRY(b200_vec_copy(r, d_b, n, st));
     B200_TRY(red_scratch(&partials, &counter));
     B200_LAUNCH(k_cg_init, red_grid(n), RED_THREADS, 0, st, n, r, dinv, z, partials, counter, sc);
+    if (ops.allreduce) B200_TRY(ops.allreduce(sc + S_ZZ, 2, st));
+    B200_LAUNCH(k_cg_post_init, 1, 1, 0, st, sc);
     B200_CUDA_TRY(cudaMemcpyAsync(h_sc, sc, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
     B200_CUDA_TRY(cudaStreamSynchronize(st));
     double dp = h_sc[S_DP];
@@ -349,17 +353,18 @@ extern "C" int b200_cg_jacobi(b200_csr_t A, const double *d_b, double *d_x, doub
     else if (dp < ttol) res->reason = (dp < atol) ? 3 : 2;
     while (!res->reason && it < max_it) {
       B200_LAUNCH(k_cg_update_p, ew_grid(n), 256, 0, st, n, z, p, sc, it == 0);
-      B200_TRY(b200_spmv(A, p, w, mode, st));
+      B200_TRY(ops.mult(p, w, st));
       B200_TRY(b200_vec_dot(p, w, n, sc + S_DPI, st));
+      if (ops.allreduce) B200_TRY(ops.allreduce(sc + S_DPI, 1, st));
       B200_TRY(red_scratch(&partials, &counter));
       B200_LAUNCH(k_cg_step, red_grid(n), RED_THREADS, 0, st, n, d_x, r, z, p, w, dinv, partials, counter, sc);
+      if (ops.allreduce) B200_TRY(ops.allreduce(sc + S_ZZ, 2, st));
       B200_LAUNCH(k_cg_rotate, 1, 1, 0, st, sc);
       B200_CUDA_TRY(cudaMemcpyAsync(h_sc, sc, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, st));
       B200_CUDA_TRY(cudaStreamSynchronize(st));
       dp = h_sc[S_DP];
       ++it;
       if (!(dp == dp)) res->reason = -9;
-      else if (h_sc[S_DPI] <= 0.0 && false) res->reason = -8;  // indefinite check is off by default in KSPCG
       else if (dp < ttol) res->reason = (dp < atol) ? 3 : 2;
     }
     if (!res->reason) res->reason = -3;  // KSP_DIVERGED_ITS
@@ -380,4 +385,21 @@ extern "C" int b200_cg_jacobi(b200_csr_t A, const double *d_b, double *d_x, doub
   cudaFree(sc);
   cudaFreeHost(h_sc);
   return rc;
+}
+}  // namespace b200
+
+extern "C" int b200_cg_jacobi(b200_csr_t A, const double *d_b, double *d_x, double rtol,
+                              double atol, int32_t max_it, int mode, b200_cg_result_t *res,
+                              void *stream)
+{
+  if (!A || !d_b || !d_x || !res) return set_error(B200_ERR_ARG, "b200_cg_jacobi: null argument");
+  B200_TRY(ensure_device());
+  b200_csr_info_t info;
+  B200_TRY(b200_csr_get_info(A, &info));
+  if (info.m != info.n) return set_error(B200_ERR_ARG, "b200_cg_jacobi: matrix must be square");
+  CgOps ops;
+  ops.m = info.m;
+  B200_TRY(b200_csr_device_arrays(A, &ops.ai, &ops.aj, &ops.aa));
+  ops.mult = [A, mode](const double *p, double *w, cudaStream_t s) { return b200_spmv(A, p, w, mode, s); };
+  return cg_jacobi_run(ops, d_b, d_x, rtol, atol, max_it, res, (cudaStream_t)stream);
 }

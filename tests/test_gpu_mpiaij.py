@@ -110,3 +110,28 @@ def test_flag_timeout_is_reported_not_hung(pk, cuda, monkeypatch):
     assert e.value.code == 77
     for m in ranks:
         m.destroy()
+
+
+def test_distributed_cg_two_gpus(pk, cuda):
+    """KSPCG + PCJACOBI over two ranks (fused MatMult_MPIAIJ + peer-window all-reduce): same
+    iteration count on every rank, within one of the single-rank oracle CG, error at O(h^2)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    torch = cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    N = 24
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "tests", "mpiaij_cg_worker.py"), str(N), "1e-10"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    r = json.loads(line)
+    p = oracle.poisson7(N)
+    _, its, _ = oracle.cg_jacobi(p["ai"], p["aj"], p["aa"], p["rhs"], rtol=1e-10, atol=1e-50, max_it=20000)
+    assert r["allreduce_ok"] and r["reason"] > 0
+    assert len(set(r["its_all"])) == 1 and abs(r["its"] - its) <= 2, (r, its)
+    assert r["linf_err"] < 0.02
