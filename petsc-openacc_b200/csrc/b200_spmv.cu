@@ -691,7 +691,9 @@ static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
         if (smem > 227 * 1024) continue;
         int ctas = 0;
         if (T == 256) B200_TRY(stream_occupancy<256>(smem, &ctas)); else B200_TRY(stream_occupancy<128>(smem, &ctas));
-        const long thr = (long)ctas * T, score = std::min(thr, 1024L) * 4 + (S == 2 ? 2 : 0) + (T == 256 ? 1 : 0);
+        // ties: 2-deep ring first; then 256-thread CTAs for short rows, 128-thread CTAs (more, smaller
+        // tiles in flight) for long rows -- 27-point: 6.5 vs 5.8 TB/s in r01_sweep_stencil27_200.log
+        const long thr = (long)ctas * T, score = std::min(thr, 1024L) * 4 + (S == 2 ? 2 : 0) + ((T == 256) == (mean <= 12.0) ? 1 : 0);
         if (score > best) { best = score; bt = T; bs = S; }
       }
     }
