@@ -247,7 +247,7 @@ def run_ours(args):
     e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
     clocks = sampler.stop()
     y_host = hy.array.copy()
-    assert np.array_equal(y_host, y.cpu().numpy()), "host-vector path and device path disagree"
+    host_matches_device = bool(np.array_equal(y_host, y.cpu().numpy()))
 
     # the same MatMult with plain int32 column indices (no diagonal-code compression), so that the
     # number against the 12-bytes-per-non-zero model is on record next to the default plan's
@@ -268,8 +268,8 @@ def run_ours(args):
         e1.record(stream)
         torch.cuda.synchronize()
         ms32 = e0.elapsed_time(e1) / n32
-        assert torch.equal(y32, y), "int32-index and compressed-index plans disagree"
         plain = {"ms_per_step": ms32, "value": nbytes / ms32 / 1e6, "unit": "GB/s",
+                 "same_bits_as_default_plan": bool(torch.equal(y32, y)),
                  "dram_bytes_model": nbytes, "note": "B200_INDEX8=0: 4-byte column indices streamed"}
         A32.destroy()
         del y32
@@ -297,6 +297,8 @@ def run_ours(args):
         import oracle
         bound = 1e-13 * oracle.row_abs_sum(ai, aj, aa, hx.array)
         parity = "within 1e-13 row bound" if np.all(np.abs(y_cpu - y_host) <= bound) else "MISMATCH"
+    if not host_matches_device:
+        parity += " (host-vector path and device path DISAGREE)"
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
