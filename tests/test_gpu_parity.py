@@ -291,3 +291,59 @@ def test_compressed_index_plan_and_equivalence(pk, cuda, monkeypatch):
     xr = gen.uniform_pm1(3000, 4)
     assert np.array_equal(_run(pk, cuda, A, xr, pk.MODE_EXACT), oracle.matmult(ai, aj, aa, xr))
     A.destroy(); A8.destroy(); A32.destroy()
+
+
+def test_edge_shapes(pk, cuda):
+    """Zero rows, zero columns, one giant row, a diagonal, strongly non-square: every entry point."""
+    torch = cuda
+    rng = np.random.default_rng(8)
+    shapes = {}
+    shapes["zero_rows"] = (np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0), 5)
+    n_big = 150_000
+    cols = np.sort(rng.choice(n_big, size=100_000, replace=False)).astype(np.int32)
+    shapes["one_giant_row"] = (np.array([0, 0, len(cols), len(cols)], np.int32), cols, rng.uniform(-1, 1, len(cols)), n_big)
+    d = 5000
+    shapes["diagonal"] = (np.arange(d + 1, dtype=np.int32), np.arange(d, dtype=np.int32), rng.uniform(-1, 1, d), d)
+    ai, aj, aa = gen.random_csr(40, 9000, 30, rng)
+    shapes["wide"] = (ai, aj, aa, 9000)
+    ai, aj, aa = gen.random_csr(9000, 40, 8, rng)
+    shapes["tall"] = (ai, aj, aa, 40)
+    for name, (ai, aj, aa, n) in shapes.items():
+        m = len(ai) - 1
+        A = pk.Csr(ai, aj, aa, n=n)
+        x, xt, y0 = gen.uniform_pm1(n, 1), gen.uniform_pm1(m, 2), gen.uniform_pm1(m, 3)
+        dx, dxt = torch.from_numpy(x).cuda(), torch.from_numpy(xt).cuda()
+        dy = torch.full((m,), float("nan"), dtype=torch.float64, device="cuda")
+        dyt = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+        for mode, fma in ((pk.MODE_EXACT, False), (pk.MODE_EXACT_FMA, True)):
+            A.mult(dx, dy, mode)
+            assert np.array_equal(dy.cpu().numpy(), oracle.matmult(ai, aj, aa, x, fma=fma)), name
+            A.mult_add(dx, torch.from_numpy(y0).cuda(), dy, mode)
+            assert np.array_equal(dy.cpu().numpy(), oracle.matmultadd(ai, aj, aa, x, y0, fma=fma)), name
+            A.mult_transpose(dxt, dyt, mode)
+            assert np.array_equal(dyt.cpu().numpy(), oracle.matmulttranspose(ai, aj, aa, xt, n, fma=fma)), name
+        A.mult(dx, dy, pk.MODE_FAST)
+        ref = oracle.matmult(ai, aj, aa, x)
+        assert np.all(np.abs(dy.cpu().numpy() - ref) <= 1e-13 * oracle.row_abs_sum(ai, aj, aa, x)), name
+        assert np.array_equal(A.mult_host(x, mode=pk.MODE_EXACT), ref), name
+        A.destroy()
+
+
+def test_argument_contract_on_device(pk, cuda):
+    """MatMult requires x != y; bad modes and null vectors are errors, not crashes."""
+    torch = cuda
+    p = oracle.poisson7(6)
+    A = pk.Csr(p["ai"], p["aj"], p["aa"])
+    v = torch.zeros(A.m, dtype=torch.float64, device="cuda")
+    w = torch.zeros(A.m, dtype=torch.float64, device="cuda")
+    with pytest.raises(pk.B200Error) as e:
+        A.mult(v, v)
+    assert e.value.code == 60
+    with pytest.raises(pk.B200Error):
+        A.mult(v, w, mode=7)
+    with pytest.raises(pk.B200Error):
+        A.mult_add(v, w, v)          # z aliases x
+    with pytest.raises(pk.B200Error):
+        A.set_kernel(99)
+    A.mult_add(v, w, w)              # z aliases y: allowed (MatMult_MPIAIJ's yy = yy + B lvec)
+    A.destroy()
