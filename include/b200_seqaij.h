@@ -120,6 +120,16 @@ int b200_spmv_transpose(b200_csr_t A, const double *d_x, double *d_y, int mode, 
 int b200_spmv_transpose_add(b200_csr_t A, const double *d_x, const double *d_z, double *d_y,
                             int mode, void *stream);
 
+/* Fused epilogues for the multigrid levels the solver options ask for (richardson(1) + jacobi,
+ * configs/PETSc_SolverOptions_GAMG.info:15-21): one pass instead of MatMult + VecAYPX (+
+ * VecPointwiseMult + VecAXPY).  Every step rounds separately, like the separate PETSc calls.   */
+/* r = b - A x                                                                                  */
+int b200_spmv_residual(b200_csr_t A, const double *d_x, const double *d_b, double *d_r, int mode,
+                       void *stream);
+/* xnew = x + dinv .* (b - A x)   (xnew must not alias x)                                       */
+int b200_spmv_jacobi_sweep(b200_csr_t A, const double *d_x, const double *d_b,
+                           const double *d_dinv, double *d_xnew, int mode, void *stream);
+
 /* ---- the hot path, HOST vectors (what MatMult_SeqAIJ(Mat,Vec,Vec) sees in PETSc 3.7.6) ----
  * x is uploaded, y downloaded, synchronous on return (the reference ends with `acc wait`,
  * src/openacc-step4/MatMult_SeqAIJ.patch:91).  Row-blocked and pipelined over three streams

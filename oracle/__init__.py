@@ -115,6 +115,22 @@ def matmulttransposeadd(ai, aj, aa, x, z, n):
     return y
 
 
+def residual(ai, aj, aa, x, b):
+    ai, aj, aa, x, b = _i32(ai), _i32(aj), _f64(aa), _f64(x), _f64(b)
+    m = len(ai) - 1
+    r = np.empty(m, dtype=np.float64)
+    lib().orc_residual(C.c_int(m), _p(ai), _p(aj), _p(aa), _p(x), _p(b), _p(r))
+    return r
+
+
+def jacobi_sweep(ai, aj, aa, x, b, dinv):
+    ai, aj, aa, x, b, dinv = _i32(ai), _i32(aj), _f64(aa), _f64(x), _f64(b), _f64(dinv)
+    m = len(ai) - 1
+    xn = np.empty(m, dtype=np.float64)
+    lib().orc_jacobi_sweep(C.c_int(m), _p(ai), _p(aj), _p(aa), _p(x), _p(b), _p(dinv), _p(xn))
+    return xn
+
+
 def row_abs_sum(ai, aj, aa, x):
     ai, aj, aa, x = _i32(ai), _i32(aj), _f64(aa), _f64(x)
     m = len(ai) - 1

@@ -19,7 +19,7 @@
  *     src/openacc-step2/MatAssemblyEnd_SeqAIJ.patch:31-37,77-79;
  *   - the problem generator follows src/helper.cpp:78-279 line by line;
  *   - the reference's only known-answer test (analytic solution, src/main_ksp.cpp:5-15,120-121)
- *     is run against this generator in tests/test_oracle_kat.py.
+ *     is run against this generator in tests/test_oracle.py (test_known_answer_analytic_solution).
  * MatMultAdd / MatMultTranspose / compressed-row / MPIAIJ setup have NO text in the reference;
  * they restate PETSc 3.7.6's published algorithm from its documented behaviour ("[P376]" below).
  *
@@ -165,6 +165,26 @@ void orc_matmulttranspose_fma(int m, int n, const int *ii, const int *aj, const 
   for (int i = 0; i < m; i++) {
     double alpha = x[i];
     for (int k = ii[i]; k < ii[i + 1]; k++) y[aj[k]] = fma(alpha, aa[k], y[aj[k]]);
+  }
+}
+
+/* The level smoother the reference's options select (configs/PETSc_SolverOptions_GAMG.info:15-21:
+ * richardson, max_it 1, bjacobi/jacobi) as PETSc runs it [P376]: r = b - A x (KSP_MatMult then
+ * VecAYPX(r,-1,b)), z = dinv .* r (VecPointwiseMult), x = x + z (VecAXPY, scale 1).  Separate
+ * calls, separately rounded. */
+void orc_residual(int m, const int *ii, const int *aj, const double *aa, const double *x,
+                  const double *b, double *r)
+{
+  orc_matmult(m, ii, aj, aa, x, r);
+  for (int i = 0; i < m; i++) r[i] = b[i] + (-1.0) * r[i];
+}
+void orc_jacobi_sweep(int m, const int *ii, const int *aj, const double *aa, const double *x,
+                      const double *b, const double *dinv, double *xnew)
+{
+  orc_residual(m, ii, aj, aa, x, b, xnew);
+  for (int i = 0; i < m; i++) {
+    double z = dinv[i] * xnew[i];
+    xnew[i]  = x[i] + z;
   }
 }
 

@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "b200_csr_create", "b200_csr_create_from_device", "b200_csr_update_values",
     "b200_csr_destroy", "b200_csr_get_info", "b200_csr_set_kernel", "b200_csr_build_transpose",
     "b200_csr_device_arrays", "b200_spmv", "b200_spmv_add", "b200_spmv_transpose",
-    "b200_spmv_transpose_add", "b200_spmv_host", "b200_spmv_add_host",
+    "b200_spmv_transpose_add", "b200_spmv_residual", "b200_spmv_jacobi_sweep", "b200_spmv_host", "b200_spmv_add_host",
     "b200_spmv_transpose_host", "b200_spmv_transpose_add_host", "b200_host_alloc", "b200_host_free", "b200_host_register",
     "b200_host_unregister", "b200_vec_set", "b200_vec_copy", "b200_vec_axpy", "b200_vec_aypx",
     "b200_vec_pointwise_mult", "b200_vec_dot", "b200_vec_norm2", "b200_vec_norm_inf",
@@ -186,6 +186,15 @@ class Csr:
         check(lib.b200_spmv_transpose_add(self._h, _dptr(x), _dptr(z), _dptr(y), C.c_int(mode),
                                           _stream(stream)))
         return y
+
+    def residual(self, x, b, r, mode=MODE_FAST, stream=None):
+        check(lib.b200_spmv_residual(self._h, _dptr(x), _dptr(b), _dptr(r), C.c_int(mode), _stream(stream)))
+        return r
+
+    def jacobi_sweep(self, x, b, dinv, xnew, mode=MODE_FAST, stream=None):
+        check(lib.b200_spmv_jacobi_sweep(self._h, _dptr(x), _dptr(b), _dptr(dinv), _dptr(xnew), C.c_int(mode),
+                                         _stream(stream)))
+        return xnew
 
     # host vectors (numpy): the MatMult_SeqAIJ(Mat,Vec,Vec) shape, synchronous
     def mult_host(self, x, y=None, mode=MODE_FAST):

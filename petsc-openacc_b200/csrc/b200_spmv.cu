@@ -105,6 +105,17 @@ __global__ void __launch_bounds__(128) k_row(int m, const int *__restrict__ ii,
   y[i] = sum;
 }
 
+// epilogue over a finished product t = A x held in y (plans without a fused epilogue)
+template <int EPI>
+__global__ void k_epilogue(int m, const double *__restrict__ x, const double *__restrict__ b,
+                           const double *__restrict__ dinv, double *y)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double r = __dsub_rn(b[i], y[i]);
+  y[i] = (EPI == 2) ? r : __dadd_rn(x[i], __dmul_rn(dinv[i], r));
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_vector: LANES lanes per row, strided partial sums, butterfly reduction.
 // ---------------------------------------------------------------------------------------------
@@ -159,12 +170,21 @@ __host__ __device__ inline size_t stream_stage_bytes(int threads, int cap, bool 
 }
 __host__ __device__ inline size_t stream_header_bytes(bool idx8) { return idx8 ? 128 + 1024 : 128; }
 
-template <int MODE, bool ADD, int THREADS, bool HALO, bool IDX8>
+// EPI: what happens to the row sum t_i = sum_k a_ik x_k before it is stored --
+//   0  y_i = t_i                          MatMult
+//   1  y_i = yin_i + ... (the accumulator STARTS at yin_i)   MatMultAdd
+//   2  y_i = b_i - t_i                    the residual of KSPRichardson / KSPInitialResidual
+//   3  y_i = x_i + dinv_i * (b_i - t_i)   one Richardson(1) + PCJACOBI sweep of the GAMG levels
+//      (configs/PETSc_SolverOptions_GAMG.info:15-21), i.e. MatMult, VecAYPX, VecPointwiseMult and
+//      VecAXPY in one pass; every step is rounded separately, as the four PETSc calls round.
+enum { EPI_NONE = 0, EPI_ADD = 1, EPI_RESIDUAL = 2, EPI_JACOBI = 3 };
+
+template <int MODE, int EPI, int THREADS, bool HALO, bool IDX8>
 __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     k_stream(const int4 *__restrict__ tiles, int ntiles, const int *__restrict__ ii,
              const int *__restrict__ aj, const double *__restrict__ aa,
              const double *__restrict__ x, const double *yin, double *y, int cap, int stages,
-             const HaloArgs h, const Idx8Args ix)
+             const HaloArgs h, const Idx8Args ix, const double *__restrict__ aux)
 {
   // HALO = MatMult_MPIAIJ in one launch:
   //  * VecScatterBegin: the first h.npush CTAs (at most one per SM) start by storing a block of this
@@ -242,7 +262,9 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     const int     *sii = reinterpret_cast<const int *>(st + aabytes + ajbytes) + (d.x & 3);
     const int      r   = d.x + tid;
     double sum = 0.0;
-    if (ADD) { if (r < d.y) sum = yin[r]; }
+    double bi = 0.0;
+    if (EPI == EPI_ADD) { if (r < d.y) sum = yin[r]; }
+    if (EPI >= EPI_RESIDUAL) { if (r < d.y) bi = yin[r]; }
     mbar_wait(&full[s], (it / stages) & 1);
     if (r < d.y) {
       const int lo = sii[tid], hi = sii[tid + 1];
@@ -262,6 +284,8 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
         for (int j = 0; j < STREAM_U; ++j)
           if ((k + j) < n) sum = acc<MODE>(sum, av[j], xv[j]);
       }
+      if (EPI == EPI_RESIDUAL) sum = __dsub_rn(bi, sum);
+      if (EPI == EPI_JACOBI) sum = __dadd_rn(__ldg(x + r), __dmul_rn(__ldg(aux + r), __dsub_rn(bi, sum)));
       y[r] = sum;
     }
     __syncwarp();
@@ -496,7 +520,12 @@ static int stream_set_attr(size_t smem)
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, ADD, THREADS, false, true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the fused residual / Jacobi-sweep epilogues (EPI 2, 3) ride on the ADD = false pass
   if (!ADD) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, 2, THREADS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, 2, THREADS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, 3, THREADS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, 3, THREADS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, false, THREADS, true, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, false, THREADS, true, true>,
@@ -962,14 +991,15 @@ extern "C" int b200_csr_device_arrays(b200_csr_t A, const int32_t **d_ai, const 
 // dispatch
 // ---------------------------------------------------------------------------------------------
 // one place that instantiates the stream kernel for (threads per CTA, halo, index width)
-template <int MODE, bool ADD, bool HALO>
+template <int MODE, int ADD, bool HALO>
 static int launch_stream_any(b200_csr_s *A, int grid, const int4 *tiles, int ntiles, const double *x,
-                             const double *yin, double *y, const HaloArgs &h, cudaStream_t st)
+                             const double *yin, double *y, const HaloArgs &h, cudaStream_t st,
+                             const double *aux = nullptr)
 {
   const Idx8Args ix{A->d_aj8, A->d_offs};
 #define B200_STREAM_GO(T, I8)                                                                       \
   B200_LAUNCH((k_stream<MODE, ADD, T, HALO, I8>), grid, T + 32, A->stream_smem, st, tiles, ntiles, \
-              A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, h, ix)
+              A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, h, ix, aux)
   if (A->idx8) { if (A->stream_threads == 256) B200_STREAM_GO(256, true); else B200_STREAM_GO(128, true); }
   else { if (A->stream_threads == 256) B200_STREAM_GO(256, false); else B200_STREAM_GO(128, false); }
 #undef B200_STREAM_GO
@@ -1094,6 +1124,45 @@ extern "C" int b200_spmv_add(b200_csr_t A, const double *d_x, const double *d_y,
   if ((d_x == d_z) && A->m) return set_error(B200_ERR_ARG, "b200_spmv_add: x and z must differ");
   B200_TRY(check_mode(mode));
   return spmv_dispatch<true>(A, d_x, d_y, d_z, mode, (cudaStream_t)stream);
+}
+
+// r = b - A x and xnew = x + dinv .* (b - A x): fused into the stream kernel's epilogue when the plan
+// is the stream kernel, otherwise MatMult followed by one element-wise kernel.
+static int spmv_epilogue(b200_csr_s *A, int epi, const double *x, const double *b, const double *dinv, double *y, int mode, cudaStream_t st)
+{
+  if (A->m == 0) return B200_OK;
+  int kernel = A->kernel_override;
+  if (!kernel) kernel = (mode == B200_MODE_FAST) ? A->kernel_fast : A->kernel_exact;
+  if (kernel == B200_KERNEL_STREAM) {
+    const HaloArgs none{};
+    if (mode == B200_MODE_EXACT) {
+      if (epi == 2) return launch_stream_any<B200_MODE_EXACT, 2, false>(A, A->stream_grid, A->d_tiles, A->ntiles, x, b, y, none, st, dinv);
+      return launch_stream_any<B200_MODE_EXACT, 3, false>(A, A->stream_grid, A->d_tiles, A->ntiles, x, b, y, none, st, dinv);
+    }
+    if (epi == 2) return launch_stream_any<B200_MODE_EXACT_FMA, 2, false>(A, A->stream_grid, A->d_tiles, A->ntiles, x, b, y, none, st, dinv);
+    return launch_stream_any<B200_MODE_EXACT_FMA, 3, false>(A, A->stream_grid, A->d_tiles, A->ntiles, x, b, y, none, st, dinv);
+  }
+  B200_TRY(spmv_dispatch<false>(A, x, nullptr, y, mode, st));
+  if (epi == 2) B200_LAUNCH((k_epilogue<2>), (A->m + 255) / 256, 256, 0, st, A->m, x, b, dinv, y);
+  else B200_LAUNCH((k_epilogue<3>), (A->m + 255) / 256, 256, 0, st, A->m, x, b, dinv, y);
+  return B200_OK;
+}
+
+extern "C" int b200_spmv_residual(b200_csr_t A, const double *d_x, const double *d_b, double *d_r, int mode, void *stream)
+{
+  if (!A || ((!d_x && A->n) || ((!d_b || !d_r) && A->m))) return set_error(B200_ERR_ARG, "b200_spmv_residual: null argument");
+  if (A->m && (d_x == d_r)) return set_error(B200_ERR_ARG, "b200_spmv_residual: x and r must differ");
+  B200_TRY(check_mode(mode));
+  return spmv_epilogue(A, 2, d_x, d_b, nullptr, d_r, mode, (cudaStream_t)stream);
+}
+
+extern "C" int b200_spmv_jacobi_sweep(b200_csr_t A, const double *d_x, const double *d_b, const double *d_dinv,
+                                      double *d_xnew, int mode, void *stream)
+{
+  if (!A || A->m != A->n || (A->m && (!d_x || !d_b || !d_dinv || !d_xnew))) return set_error(B200_ERR_ARG, "b200_spmv_jacobi_sweep: bad argument (square matrix, non-null vectors)");
+  if (A->m && d_x == d_xnew) return set_error(B200_ERR_ARG, "b200_spmv_jacobi_sweep: x and xnew must differ (other rows still read x)");
+  B200_TRY(check_mode(mode));
+  return spmv_epilogue(A, 3, d_x, d_b, d_dinv, d_xnew, mode, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------

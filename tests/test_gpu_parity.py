@@ -347,3 +347,37 @@ def test_argument_contract_on_device(pk, cuda):
         A.set_kernel(99)
     A.mult_add(v, w, w)              # z aliases y: allowed (MatMult_MPIAIJ's yy = yy + B lvec)
     A.destroy()
+
+
+@pytest.mark.parametrize("name", ["poisson7_50", "stencil27_16", "powerlaw_20k", "random_ragged"])
+def test_fused_residual_and_jacobi_sweep(pk, cuda, name):
+    """r = b - A x and xnew = x + dinv.*(b - A x) in one pass: the same bits as PETSc's separate
+    MatMult, VecAYPX, VecPointwiseMult, VecAXPY (oracle.residual / oracle.jacobi_sweep)."""
+    torch = cuda
+    ai, aj, aa, n = CASES[name]
+    m = len(ai) - 1
+    if m != n:   # the sweep needs a square operator; the residual does not
+        x, b = gen.uniform_pm1(n, 1), gen.uniform_pm1(m, 2)
+        A = pk.Csr(ai, aj, aa, n=n)
+        r = torch.empty(m, dtype=torch.float64, device="cuda")
+        A.residual(torch.from_numpy(x).cuda(), torch.from_numpy(b).cuda(), r, pk.MODE_EXACT)
+        assert np.array_equal(r.cpu().numpy(), oracle.residual(ai, aj, aa, x, b))
+        A.destroy()
+        return
+    x, b = gen.uniform_pm1(n, 1), gen.uniform_pm1(m, 2)
+    dinv = 1.0 / (1.5 + gen.uniform_pm1(m, 3))
+    A = pk.Csr(ai, aj, aa, n=n)
+    dx, db, dd = (torch.from_numpy(v).cuda() for v in (x, b, dinv))
+    out = torch.full((m,), float("nan"), dtype=torch.float64, device="cuda")
+    kernels = [None, pk.KERNEL_ROW] + ([pk.KERNEL_STREAM] if A.info().stream_tiles else [])
+    for k in kernels:
+        if k is not None:
+            A.set_kernel(k)
+        A.residual(dx, db, out, pk.MODE_EXACT)
+        assert np.array_equal(out.cpu().numpy(), oracle.residual(ai, aj, aa, x, b)), (name, k)
+        A.jacobi_sweep(dx, db, dd, out, pk.MODE_EXACT)
+        assert np.array_equal(out.cpu().numpy(), oracle.jacobi_sweep(ai, aj, aa, x, b, dinv)), (name, k)
+        A.set_kernel(pk.KERNEL_AUTO)
+    with pytest.raises(pk.B200Error):
+        A.jacobi_sweep(dx, db, dd, dx, pk.MODE_EXACT)   # in place is an error: other rows still read x
+    A.destroy()
