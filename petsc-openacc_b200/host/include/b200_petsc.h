@@ -151,6 +151,17 @@ PetscErrorCode MatDestroy(Mat *A);
 PetscErrorCode MatSeqAIJGetCSRB200(Mat A, PetscInt *m, PetscInt *n, PetscInt *nz, const PetscInt **i, const PetscInt **j, const PetscScalar **a);
 PetscErrorCode MatSeqAIJGetInfoB200(Mat A, PetscInt *nonzerorowcnt, PetscInt *rmax, PetscBool *compressedrow, PetscInt *cprow_nrows, PetscInt *fshift);
 
+/* ---- input formats: PETSc binary (MatLoad / VecLoad) and MatrixMarket ----------------------- */
+typedef struct _p_PetscViewer *PetscViewer;
+typedef enum { FILE_MODE_READ, FILE_MODE_WRITE, FILE_MODE_APPEND, FILE_MODE_UPDATE, FILE_MODE_APPEND_UPDATE } PetscFileMode;
+#define PETSC_ERR_FILE_UNEXPECTED 79
+PetscErrorCode PetscViewerBinaryOpen(MPI_Comm, const char name[], PetscFileMode mode, PetscViewer *viewer);
+PetscErrorCode PetscViewerDestroy(PetscViewer *viewer);
+/* PETSc 3.7.6 signature is MatLoad(Mat, PetscViewer) on a created Mat; here the Mat is created by the call */
+PetscErrorCode MatLoad(Mat *newmat, PetscViewer viewer);
+PetscErrorCode VecLoad(Vec *newvec, PetscViewer viewer);
+PetscErrorCode MatLoadMatrixMarketB200(const char path[], Mat *newmat);
+
 /* ---- DMDA (what src/helper.cpp uses) ------------------------------------------------------- */
 typedef struct _p_DM *DM;
 typedef struct _p_ISLocalToGlobalMapping *ISLocalToGlobalMapping;
