@@ -9,11 +9,18 @@
 // which makes the fast path of short-row matrices bit-reproducible against the CPU loop.
 //
 // Kernels (all fp64 values, int32 indices):
-//   k_row     thread per row from global memory          -- the reference's launch shape
-//   k_stream  bulk-copy staged CSR tiles, thread per row -- default for short, regular rows
-//   k_vector  LANES lanes per row + __shfl_xor reduction -- medium rows
-//   k_cprow   compressed-row (only non-empty rows)       -- off-diagonal block B of MPIAIJ
+//   k_stream  bulk-copy staged CSR tiles, thread per row -- default for short, regular rows; template
+//             flags: EPI (MatMult / MatMultAdd / residual / Jacobi sweep), HALO (MatMult_MPIAIJ in one
+//             launch: NVLink push + A x + ghost rows), IDX8 (1-byte diagonal codes instead of int32 columns)
+//   k_merge   nnz-balanced tiles + deterministic carry fix-up -- skewed row lengths
+//   k_row     thread per row from global memory          -- the reference's launch shape; EXACT fallback
+//   k_vector  LANES lanes per row + __shfl_xor reduction -- override / comparison
+//   k_cprow   compressed-row (only non-empty rows)       -- matrices with >= 60 % empty rows
 //   k_tr_atomic  A^T x by fp64 atomics                   -- transpose without a second copy
+// Why no SELL-C-sigma / sliced-ELL copy: staging the CSR tile in shared memory already gives what
+// those formats buy on a GPU -- the matrix is read in fully coalesced 16-byte-aligned bulk copies and
+// lane = consecutive row makes the x gathers of a stencil contiguous -- without padding, without a
+// second copy of the values, and while keeping the row's CSR order, i.e. the reference's bits.
 #include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
