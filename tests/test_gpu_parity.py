@@ -381,3 +381,84 @@ def test_fused_residual_and_jacobi_sweep(pk, cuda, name):
     with pytest.raises(pk.B200Error):
         A.jacobi_sweep(dx, db, dd, dx, pk.MODE_EXACT)   # in place is an error: other rows still read x
     A.destroy()
+
+
+def test_create_from_device_arrays(pk, cuda):
+    torch = cuda
+    p = oracle.poisson7(14)
+    d_ai, d_aj, d_aa = (torch.from_numpy(p[k]).cuda() for k in ("ai", "aj", "aa"))
+    A = pk.Csr.from_device(d_ai, d_aj, d_aa, 14 ** 3, 14 ** 3)
+    assert A.nz == len(p["aj"]) and A.info().stream_tiles > 0 and A.info().index8_diagonals == 0
+    x = gen.uniform_pm1(14 ** 3, 2)
+    dy = torch.empty(14 ** 3, dtype=torch.float64, device="cuda")
+    A.mult(torch.from_numpy(x).cuda(), dy, pk.MODE_EXACT)
+    assert np.array_equal(dy.cpu().numpy(), oracle.matmult(p["ai"], p["aj"], p["aa"], x))
+    A.destroy()
+
+
+def test_transpose_by_atomics(pk, cuda, monkeypatch):
+    """FAST-mode A^T x without the explicit transpose copy (fp64 RED.ADD): within the column bound."""
+    torch = cuda
+    monkeypatch.setenv("B200_TRANSPOSE_ATOMIC", "1")
+    ai, aj, aa, n = CASES["random_ragged"]
+    m = len(ai) - 1
+    A = pk.Csr(ai, aj, aa, n=n)
+    x, z = gen.uniform_pm1(m, 5), gen.uniform_pm1(n, 6)
+    dx, dz = torch.from_numpy(x).cuda(), torch.from_numpy(z).cuda()
+    dy = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    absb = np.zeros(n)
+    np.add.at(absb, aj, np.abs(aa * np.repeat(x, np.diff(ai))))
+    A.mult_transpose(dx, dy, pk.MODE_FAST)
+    assert not A.info().has_transpose
+    assert np.all(np.abs(dy.cpu().numpy() - oracle.matmulttranspose(ai, aj, aa, x, n)) <= TOL * absb)
+    A.mult_transpose_add(dx, dz, dy, pk.MODE_FAST)
+    assert np.all(np.abs(dy.cpu().numpy() - oracle.matmulttransposeadd(ai, aj, aa, x, z, n)) <= TOL * (absb + np.abs(z)))
+    A.mult_transpose(dx, dy, pk.MODE_EXACT)          # EXACT always goes through the explicit copy
+    assert A.info().has_transpose
+    assert np.array_equal(dy.cpu().numpy(), oracle.matmulttranspose(ai, aj, aa, x, n))
+    A.destroy()
+
+
+def test_vector_kernels_direct(pk, cuda):
+    torch = cuda
+    for n in (1, 31, 1000, 1_000_003):
+        a, b = gen.uniform_pm1(n, 1), gen.uniform_pm1(n, 2)
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        pk.vec_dot(da, db, out)
+        assert abs(out.item() - float(np.dot(a, b))) <= 1e-12 * float(np.abs(a * b).sum()) + 1e-300
+        first = out.item()
+        pk.vec_dot(da, db, out)
+        assert out.item() == first                      # deterministic reduction
+        pk.vec_norm2(da, out)
+        assert abs(out.item() - float(np.linalg.norm(a))) <= 1e-13 * float(np.linalg.norm(a)) + 1e-300
+        pk.vec_norm_inf(da, out)
+        assert out.item() == float(np.abs(a).max())
+        pk.vec_sum(da, out)
+        assert abs(out.item() - float(a.sum())) <= 1e-12 * float(np.abs(a).sum()) + 1e-300
+        dw = torch.empty_like(da)
+        pk.vec_pointwise_mult(dw, da, db)
+        assert np.array_equal(dw.cpu().numpy(), a * b)
+        pk.vec_copy(dw, da)
+        pk.vec_axpy(dw, 0.5, db)
+        assert np.allclose(dw.cpu().numpy(), a + 0.5 * b, rtol=0, atol=1e-15)
+        pk.vec_aypx(dw, -1.0, db)
+        assert np.allclose(dw.cpu().numpy(), b - (a + 0.5 * b), rtol=0, atol=1e-15)
+        pk.vec_set(dw, 3.25)
+        assert np.all(dw.cpu().numpy() == 3.25)
+
+
+def test_registered_pageable_host_vectors(pk, cuda):
+    """cudaHostRegister route for Vec arrays PETSc allocated itself (real-PETSc route)."""
+    import ctypes as C
+    p = oracle.poisson7(20)
+    A = pk.Csr(p["ai"], p["aj"], p["aa"])
+    x = np.ascontiguousarray(gen.uniform_pm1(A.n, 1))
+    y = np.empty(A.m)
+    pk.check(pk.lib.b200_host_register(x.ctypes.data_as(C.c_void_p), C.c_size_t(x.nbytes)))
+    pk.check(pk.lib.b200_host_register(y.ctypes.data_as(C.c_void_p), C.c_size_t(y.nbytes)))
+    A.mult_host(x, y, pk.MODE_EXACT)
+    assert np.array_equal(y, oracle.matmult(p["ai"], p["aj"], p["aa"], x))
+    pk.check(pk.lib.b200_host_unregister(x.ctypes.data_as(C.c_void_p)))
+    pk.check(pk.lib.b200_host_unregister(y.ctypes.data_as(C.c_void_p)))
+    A.destroy()
