@@ -8,9 +8,19 @@
 #include <functional>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/b200_seqaij.h"
 
 namespace b200 {
+
+// NVTX ranges around the C-ABI calls (B200_NVTX=1): the counterpart of the reference's Score-P /
+// nvprof instrumented builds (Makefile:137-150, runs/single-node-nvprof.pbs) for nsys / ncu.
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char *name);
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 
 extern thread_local std::string g_last_error;
 extern std::atomic<uint64_t>    g_launches;

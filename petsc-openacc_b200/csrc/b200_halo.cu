@@ -302,6 +302,7 @@ static int up(T **d, const std::vector<T> &h)
 
 extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
 {
+  NvtxRange nvtx_("b200_mpiaij_upload");
   if (!M) return set_error(B200_ERR_ARG, "null handle");
   if (M->uploaded) return B200_OK;
   B200_TRY(ensure_device());
@@ -506,6 +507,7 @@ extern "C" int b200_mpiaij_mult_finish(b200_mpiaij_t M, const double *d_x, doubl
 
 extern "C" int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream)
 {
+  NvtxRange nvtx_("b200_mpiaij_mult");
   if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
   cudaStream_t st = (cudaStream_t)stream;
   B200_TRY(prepare_push(M));
@@ -604,6 +606,7 @@ extern "C" int b200_mpiaij_set_rank_window(b200_mpiaij_t M, int32_t q, const voi
 
 extern "C" int b200_mpiaij_allreduce_sum(b200_mpiaij_t M, double *d_vals, int32_t nvals, void *stream)
 {
+  NvtxRange nvtx_("b200_mpiaij_allreduce_sum");
   if (!M || !M->uploaded || !d_vals || nvals < 1 || nvals > RED_MAX_VALS) return set_error(B200_ERR_ARG, "b200_mpiaij_allreduce_sum: bad argument");
   if (M->size == 1) return B200_OK;
   if (M->all_windows.empty()) return set_error(B200_ERR_STATE, "b200_mpiaij_set_rank_window for every rank first");
@@ -624,6 +627,7 @@ extern "C" int b200_mpiaij_allreduce_sum(b200_mpiaij_t M, double *d_vals, int32_
 extern "C" int b200_mpiaij_cg_jacobi(b200_mpiaij_t M, const double *d_b, double *d_x, double rtol, double atol,
                                      int32_t max_it, int mode, b200_cg_result_t *res, void *stream)
 {
+  NvtxRange nvtx_("b200_mpiaij_cg_jacobi");
   if (!M || !M->uploaded || !d_b || !d_x || !res) return set_error(B200_ERR_ARG, "b200_mpiaij_cg_jacobi: bad argument");
   CgOps ops;
   ops.m = M->nloc;

@@ -53,6 +53,13 @@ int env_int(const char *name, int dflt)
   return (s && *s) ? atoi(s) : dflt;
 }
 
+NvtxRange::NvtxRange(const char *name)
+{
+  static const int enabled = env_int("B200_NVTX", 0);
+  on = enabled != 0;
+  if (on) nvtxRangePushA(name);
+}
+
 static int g_sm_count = 0;
 static int g_dev_ok   = -1;
 
@@ -876,6 +883,7 @@ static int fill_ai_tail(b200_csr_s *A)
 extern "C" int b200_csr_create(b200_csr_t *out, int32_t m, int32_t n, const int32_t *h_ai,
                                const int32_t *h_aj, const double *h_aa)
 {
+  NvtxRange nvtx_("b200_csr_create");
   if (!out || m < 0 || n < 0 || !h_ai) return set_error(B200_ERR_ARG, "b200_csr_create: bad argument");
   B200_TRY(ensure_device());
   const int32_t nz = h_ai[m];
@@ -1118,6 +1126,7 @@ static int check_mode(int mode)
 
 extern "C" int b200_spmv(b200_csr_t A, const double *d_x, double *d_y, int mode, void *stream)
 {
+  NvtxRange nvtx_("b200_spmv");
   if (!A || (!d_x && A->n) || (!d_y && A->m)) return set_error(B200_ERR_ARG, "b200_spmv: null argument");
   if (d_x == d_y && A->m) return set_error(B200_ERR_ARG, "b200_spmv: x and y must differ (MatMult contract)");
   B200_TRY(check_mode(mode));
@@ -1127,6 +1136,7 @@ extern "C" int b200_spmv(b200_csr_t A, const double *d_x, double *d_y, int mode,
 extern "C" int b200_spmv_add(b200_csr_t A, const double *d_x, const double *d_y, double *d_z,
                              int mode, void *stream)
 {
+  NvtxRange nvtx_("b200_spmv_add");
   if (!A || (!d_x && A->n) || ((!d_y || !d_z) && A->m)) return set_error(B200_ERR_ARG, "b200_spmv_add: null argument");
   if ((d_x == d_z) && A->m) return set_error(B200_ERR_ARG, "b200_spmv_add: x and z must differ");
   B200_TRY(check_mode(mode));
@@ -1157,6 +1167,7 @@ static int spmv_epilogue(b200_csr_s *A, int epi, const double *x, const double *
 
 extern "C" int b200_spmv_residual(b200_csr_t A, const double *d_x, const double *d_b, double *d_r, int mode, void *stream)
 {
+  NvtxRange nvtx_("b200_spmv_residual");
   if (!A || ((!d_x && A->n) || ((!d_b || !d_r) && A->m))) return set_error(B200_ERR_ARG, "b200_spmv_residual: null argument");
   if (A->m && (d_x == d_r)) return set_error(B200_ERR_ARG, "b200_spmv_residual: x and r must differ");
   B200_TRY(check_mode(mode));
@@ -1166,6 +1177,7 @@ extern "C" int b200_spmv_residual(b200_csr_t A, const double *d_x, const double 
 extern "C" int b200_spmv_jacobi_sweep(b200_csr_t A, const double *d_x, const double *d_b, const double *d_dinv,
                                       double *d_xnew, int mode, void *stream)
 {
+  NvtxRange nvtx_("b200_spmv_jacobi_sweep");
   if (!A || A->m != A->n || (A->m && (!d_x || !d_b || !d_dinv || !d_xnew))) return set_error(B200_ERR_ARG, "b200_spmv_jacobi_sweep: bad argument (square matrix, non-null vectors)");
   if (A->m && d_x == d_xnew) return set_error(B200_ERR_ARG, "b200_spmv_jacobi_sweep: x and xnew must differ (other rows still read x)");
   B200_TRY(check_mode(mode));
@@ -1178,6 +1190,7 @@ extern "C" int b200_spmv_jacobi_sweep(b200_csr_t A, const double *d_x, const dou
 // ---------------------------------------------------------------------------------------------
 extern "C" int b200_csr_build_transpose(b200_csr_t A)
 {
+  NvtxRange nvtx_("b200_csr_build_transpose");
   if (!A) return set_error(B200_ERR_ARG, "null handle");
   if (A->T) return B200_OK;
   const int m = A->m, n = A->n, nz = A->nz;
@@ -1235,6 +1248,7 @@ static int transpose_common(b200_csr_s *A, const double *d_x, const double *d_z,
 
 extern "C" int b200_spmv_transpose(b200_csr_t A, const double *d_x, double *d_y, int mode, void *stream)
 {
+  NvtxRange nvtx_("b200_spmv_transpose");
   if (!A || (!d_x && A->m) || (!d_y && A->n)) return set_error(B200_ERR_ARG, "b200_spmv_transpose: null argument");
   return transpose_common(A, d_x, nullptr, d_y, mode, (cudaStream_t)stream);
 }
@@ -1242,6 +1256,7 @@ extern "C" int b200_spmv_transpose(b200_csr_t A, const double *d_x, double *d_y,
 extern "C" int b200_spmv_transpose_add(b200_csr_t A, const double *d_x, const double *d_z,
                                        double *d_y, int mode, void *stream)
 {
+  NvtxRange nvtx_("b200_spmv_transpose_add");
   if (!A || (!d_x && A->m) || ((!d_y || !d_z) && A->n)) return set_error(B200_ERR_ARG, "b200_spmv_transpose_add: null argument");
   return transpose_common(A, d_x, d_z, d_y, mode, (cudaStream_t)stream);
 }
@@ -1318,6 +1333,7 @@ static bool host_pipeline_applies(b200_csr_s *A, int mode)
 
 extern "C" int b200_spmv_host(b200_csr_t A, const double *h_x, double *h_y, int mode)
 {
+  NvtxRange nvtx_("b200_spmv_host");
   if (!A || (!h_x && A->n) || (!h_y && A->m)) return set_error(B200_ERR_ARG, "b200_spmv_host: null argument");
   B200_TRY(check_mode(mode));
   B200_TRY(host_scratch(A, A->n, A->m));

@@ -392,6 +392,7 @@ extern "C" int b200_cg_jacobi(b200_csr_t A, const double *d_b, double *d_x, doub
                               double atol, int32_t max_it, int mode, b200_cg_result_t *res,
                               void *stream)
 {
+  NvtxRange nvtx_("b200_cg_jacobi");
   if (!A || !d_b || !d_x || !res) return set_error(B200_ERR_ARG, "b200_cg_jacobi: null argument");
   B200_TRY(ensure_device());
   b200_csr_info_t info;
