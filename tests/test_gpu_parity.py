@@ -462,3 +462,43 @@ def test_registered_pageable_host_vectors(pk, cuda):
     pk.check(pk.lib.b200_host_unregister(x.ctypes.data_as(C.c_void_p)))
     pk.check(pk.lib.b200_host_unregister(y.ctypes.data_as(C.c_void_p)))
     A.destroy()
+
+
+@pytest.mark.parametrize("name", ["poisson7_20", "stencil27_16", "powerlaw_20k", "random_ragged", "mostly_empty", "long_rows"])
+def test_no_write_outside_the_output_vector(pk, cuda, name):
+    """compute-sanitizer is closed on this pool: guard bands around y (and around lvec-sized scratch)
+    must keep their sentinel through every kernel and epilogue."""
+    torch = cuda
+    ai, aj, aa, n = CASES[name]
+    m = len(ai) - 1
+    A = pk.Csr(ai, aj, aa, n=n)
+    G = 4096
+    sentinel = -7.25e300
+    buf = torch.full((m + 2 * G,), sentinel, dtype=torch.float64, device="cuda")
+    y = buf[G:G + m]
+    bt = torch.full((n + 2 * G,), sentinel, dtype=torch.float64, device="cuda")
+    yt = bt[G:G + n]
+    x = torch.from_numpy(gen.uniform_pm1(n, 1)).cuda()
+    xt = torch.from_numpy(gen.uniform_pm1(m, 2)).cuda()
+    y0 = torch.from_numpy(gen.uniform_pm1(m, 3)).cuda()
+    info = A.info()
+    kernels = [pk.KERNEL_ROW, pk.KERNEL_VECTOR, pk.KERNEL_MERGE]
+    if info.stream_tiles:
+        kernels.append(pk.KERNEL_STREAM)
+    if info.compressedrow_use:
+        kernels.append(pk.KERNEL_CPROW)
+    for k in kernels:
+        A.set_kernel(k)
+        mode = pk.MODE_FAST if k in (pk.KERNEL_VECTOR, pk.KERNEL_MERGE) else pk.MODE_EXACT
+        A.mult(x, y, mode)
+        A.mult_add(x, y0, y, mode)
+    A.set_kernel(pk.KERNEL_AUTO)
+    A.mult_transpose(xt, yt, pk.MODE_EXACT)
+    if m == n:
+        A.residual(x, y0, y, pk.MODE_EXACT)
+        A.jacobi_sweep(x, y0, y0, y, pk.MODE_EXACT)
+    torch.cuda.synchronize()
+    for b, k in ((buf, m), (bt, n)):
+        assert bool((b[:G] == sentinel).all()) and bool((b[G + k:] == sentinel).all()), name
+    assert not bool((y == sentinel).any()) and not bool((yt == sentinel).any())
+    A.destroy()
