@@ -183,6 +183,14 @@ int b200_gen_poisson7_bases(int M, int N, int P, int size, int32_t *base /* size
 int b200_gen_poisson7(int M, int N, int P, int size, int rank, int refpoint, int32_t *ai,
                       int32_t *aj_global, double *aa, double *rhs, double *exact);
 
+/* BASELINE configs[4]: power-law row lengths 1..lmax (alpha = 2 -> mean ~ ln lmax), columns = sorted
+ * unique splitmix64 draws mod n, values uniform [-1,1).  First the row pointers (ai[m+1]), then the
+ * fill into arrays of ai[m] entries.                                                              */
+int b200_gen_powerlaw_rowptr(int32_t m, int32_t n, double alpha, int32_t lmax, uint64_t seed,
+                             int32_t *ai);
+int b200_gen_powerlaw_fill(int32_t m, int32_t n, double alpha, int32_t lmax, uint64_t seed,
+                           const int32_t *ai, int32_t *aj, double *aa);
+
 #ifdef __cplusplus
 }
 #endif

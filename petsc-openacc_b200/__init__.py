@@ -430,4 +430,18 @@ def gen_poisson7(M, size=1, rank=0, refpoint=True, vectors=False):
     return dict(ai=ai, aj=aj, aa=aa, rhs=rhs, exact=ex, rstart=rstart, base=base, info=out)
 
 
-ABI_SYMBOLS += ["b200_gen_poisson7_info", "b200_gen_poisson7_bases", "b200_gen_poisson7"]
+ABI_SYMBOLS += ["b200_gen_poisson7_info", "b200_gen_poisson7_bases", "b200_gen_poisson7",
+                "b200_gen_powerlaw_rowptr", "b200_gen_powerlaw_fill"]
+
+
+def gen_powerlaw(m, n=None, alpha=2.0, lmax=10000, seed=0x5EED):
+    """The irregular matrix of BASELINE configs[4] from the product generator (threaded C++)."""
+    n = m if n is None else n
+    ai = np.zeros(m + 1, np.int32)
+    check(lib.b200_gen_powerlaw_rowptr(C.c_int32(m), C.c_int32(n), C.c_double(alpha), C.c_int32(lmax),
+                                       C.c_uint64(seed), _np_ptr(ai)))
+    aj = np.zeros(int(ai[-1]), np.int32)
+    aa = np.zeros(int(ai[-1]))
+    check(lib.b200_gen_powerlaw_fill(C.c_int32(m), C.c_int32(n), C.c_double(alpha), C.c_int32(lmax),
+                                     C.c_uint64(seed), _np_ptr(ai), _np_ptr(aj), _np_ptr(aa)))
+    return ai, aj, aa

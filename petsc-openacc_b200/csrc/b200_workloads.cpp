@@ -247,3 +247,69 @@ extern "C" int b200_gen_poisson7(int M, int N, int P, int size, int rank, int re
   }
   return B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic irregular matrix of BASELINE configs[4]: m x n, row length
+// L_i = min(lmax, max(1, floor(u_i^(-1/(alpha-1))))), columns = sorted unique splitmix64 draws mod n,
+// values uniform [-1,1) indexed by the final non-zero position.  Counter based: identical to
+// tests/gen.py::powerlaw for the same arguments.  Two calls: sizes (ai filled), then fill.
+// ---------------------------------------------------------------------------------------------
+namespace {
+inline uint64_t splitmix64(uint64_t z)
+{
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+inline int powerlaw_row(uint64_t seed, int64_t n, double alpha, int lmax, int64_t row, std::vector<int32_t> &cols)
+{
+  double u = (double)(splitmix64(seed ^ (uint64_t)row) >> 11) / 9007199254740992.0;
+  if (u < 1e-300) u = 1e-300;
+  double Ld = std::floor(std::pow(u, -1.0 / (alpha - 1.0)));
+  int64_t L = (int64_t)std::min<double>((double)lmax, std::max(1.0, Ld));
+  L = std::min<int64_t>(L, n);
+  cols.resize((size_t)L);
+  const uint64_t s2 = seed * 0x100000001B3ull;
+  for (int64_t k = 0; k < L; ++k) cols[(size_t)k] = (int32_t)(splitmix64(s2 ^ ((uint64_t)row << 20) ^ (uint64_t)k) % (uint64_t)n);
+  std::sort(cols.begin(), cols.end());
+  cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+  return (int)cols.size();
+}
+}  // namespace
+
+extern "C" int b200_gen_powerlaw_rowptr(int32_t m, int32_t n, double alpha, int32_t lmax, uint64_t seed, int32_t *ai)
+{
+  if (m < 0 || n < 1 || !ai || alpha <= 1.0 || lmax < 1) return set_error(B200_ERR_ARG, "b200_gen_powerlaw_rowptr: bad argument");
+  parallel_for(m, [&](int a, int b) {
+    std::vector<int32_t> cols;
+    for (int r = a; r < b; ++r) ai[r + 1] = powerlaw_row(seed, n, alpha, lmax, r, cols);
+  });
+  ai[0] = 0;
+  long long tot = 0;
+  for (int r = 0; r < m; ++r) {
+    tot += ai[r + 1];
+    if (tot > 2147483647LL) return set_error(B200_ERR_ARG, "power-law matrix exceeds int32 non-zeros");
+    ai[r + 1] = (int32_t)tot;
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_gen_powerlaw_fill(int32_t m, int32_t n, double alpha, int32_t lmax, uint64_t seed, const int32_t *ai,
+                                      int32_t *aj, double *aa)
+{
+  if (m < 0 || n < 1 || !ai || !aj || !aa) return set_error(B200_ERR_ARG, "b200_gen_powerlaw_fill: bad argument");
+  const uint64_t vseed = seed ^ 0xABCDEFull;
+  parallel_for(m, [&](int a, int b) {
+    std::vector<int32_t> cols;
+    for (int r = a; r < b; ++r) {
+      powerlaw_row(seed, n, alpha, lmax, r, cols);
+      for (size_t k = 0; k < cols.size(); ++k) {
+        const int64_t p = (int64_t)ai[r] + (int64_t)k;
+        aj[p] = cols[k];
+        aa[p] = (double)(splitmix64(vseed ^ (uint64_t)p) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+      }
+    }
+  });
+  return B200_OK;
+}

@@ -61,5 +61,5 @@ if which == "27":
     run(f"27-point {N}^3", ai, aj, aa, N ** 3)
 else:
     M = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
-    t0 = time.time(); ai, aj, aa = gen.powerlaw(M); print(f"generated in {time.time()-t0:.0f}s")
+    t0 = time.time(); ai, aj, aa = pk.gen_powerlaw(M); print(f"generated in {time.time()-t0:.0f}s")
     run(f"power-law {M}", ai, aj, aa, M, transpose=True)

@@ -39,3 +39,12 @@ def test_gen_vector_matches_definition(pk):
     assert np.array_equal(pk.gen_vector(1000, 0xB200), gen.uniform_pm1(1000, 0xB200))
     x = pk.gen_vector(100000, 5)
     assert x.min() >= -1.0 and x.max() < 1.0 and abs(x.mean()) < 0.02
+
+
+@pytest.mark.parametrize("m,lmax", [(2000, 300), (50000, 10000), (300, 1000)])
+def test_powerlaw_generator_matches_definition(pk, m, lmax):
+    ai, aj, aa = pk.gen_powerlaw(m, lmax=lmax)
+    ri, rj, ra = gen.powerlaw(m, lmax=lmax)
+    assert np.array_equal(ai, ri) and np.array_equal(aj, rj) and np.array_equal(aa, ra)
+    lens = np.diff(ai)
+    assert lens.min() >= 1 and lens.max() <= min(lmax, m)

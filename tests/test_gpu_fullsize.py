@@ -121,7 +121,7 @@ def test_300_cubed_eight_rank_decomposition_on_one_gpu(pk, cuda):
 
 def test_powerlaw_1m_merge_and_transpose(pk, cuda):
     torch = cuda
-    ai, aj, aa = gen.powerlaw(1_000_000)
+    ai, aj, aa = pk.gen_powerlaw(1_000_000)   # product generator (== tests/gen.py::powerlaw, tests/test_generator.py)
     m = len(ai) - 1
     A = pk.Csr(ai, aj, aa)
     assert pk.KERNEL_NAMES[A.info().kernel_fast] == "merge"
