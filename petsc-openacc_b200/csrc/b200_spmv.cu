@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
 #define MERGE_CAP 2048
 #define MERGE_RCAP 1024
 #define MERGE_THREADS 256
+#define MERGEX_LONG 96
 
 template <bool ADD>
 __global__ void __launch_bounds__(MERGE_THREADS)
@@ -408,6 +409,101 @@ __global__ void k_merge_fixup(int nsplit, const int4 *__restrict__ split, const 
   double     sum = tail[sp.y];
   for (int t = sp.y + 1; t <= sp.z; ++t) sum += head[t];
   y[sp.x] = ADD ? yin[sp.x] + sum : sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_mergex / k_longrow: the EXACT summation order on skewed matrices at merge-kernel speed.
+// Tiles hold WHOLE rows only (at most MERGE_CAP non-zeros, MERGE_RCAP rows); the CTA stages a and
+// x[aj] side by side in shared memory, coalesced over non-zeros, then one thread per row adds the
+// row left to right (unfused or fma, like the oracle).  Rows beyond MERGEX_LONG entries go to k_longrow:
+// one warp per row loads 32 (a, x) pairs at a time and every lane replays the 32 adds in order
+// through shuffles -- the chain is as long as on one thread, but the loads are coalesced.
+// xtiles[t] = {first row, last row + 1, ai[first], ai[last + 1]}.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, bool ADD>
+__global__ void __launch_bounds__(MERGE_THREADS)
+    k_mergex(const int4 *__restrict__ tiles, const int *__restrict__ ii, const int *__restrict__ aj,
+             const double *__restrict__ aa, const double *__restrict__ x, const double *yin, double *y)
+{
+  // EXACT rounds the product on its own, so the product is what gets staged (half the shared
+  // memory, twice the CTAs per SM); EXACT_FMA needs a and x side by side for the fused chain
+  constexpr bool PROD = (MODE == B200_MODE_EXACT);
+  __shared__ double sa[MERGE_CAP];
+  __shared__ double sx[PROD ? 1 : MERGE_CAP];
+  __shared__ int    rp[MERGE_RCAP + 1];
+  const int4 d   = __ldg(tiles + blockIdx.x);
+  const int  tid = threadIdx.x, nr = d.y - d.x, s = d.z, n = d.w - d.z;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  for (int j = tid; j <= nr; j += MERGE_THREADS) rp[j] = __ldg(ii + d.x + j) - s;
+  {
+    constexpr int PER = MERGE_CAP / MERGE_THREADS;
+    int    c[PER];
+    double a[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int k = tid + i * MERGE_THREADS;
+      c[i] = (k < n) ? ldg_s32_stream_policy(aj + s + k, pol_stream) : 0;
+      a[i] = (k < n) ? ldg_f64_stream_policy(aa + s + k, pol_stream) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int k = tid + i * MERGE_THREADS;
+      if (k < n) {
+        const double xv = ldg_f64_policy(x + c[i], pol_keep);
+        if (PROD) sa[k] = __dmul_rn(a[i], xv);
+        else { sa[k] = a[i]; sx[k] = xv; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < nr; j += MERGE_THREADS) {
+    const int r   = d.x + j;
+    double    sum = ADD ? yin[r] : 0.0;
+    if (PROD) for (int k = rp[j]; k < rp[j + 1]; ++k) sum = __dadd_rn(sum, sa[k]);
+    else for (int k = rp[j]; k < rp[j + 1]; ++k) sum = __fma_rn(sa[k], sx[k], sum);
+    y[r] = sum;
+  }
+}
+
+// One warp per long row: the lanes fetch 32 (a, x) pairs at a time, coalesced, and park them (or
+// their rounded products) in shared memory; lane 0 alone runs the ordered chain out of shared
+// memory while the next 32 pairs are already in flight.  (Replaying the chain on all lanes through
+// shuffles was shuffle-throughput bound: 1.5 ms for the 46 M long-row entries of configs[4].)
+template <int MODE, bool ADD>
+__global__ void __launch_bounds__(128)
+    k_longrow(int nlong, const int *__restrict__ rows, const int *__restrict__ ii, const int *__restrict__ aj,
+              const double *__restrict__ aa, const double *__restrict__ x, const double *yin, double *y)
+{
+  constexpr bool PROD = (MODE == B200_MODE_EXACT);
+  __shared__ double sa[4][2][32];
+  __shared__ double sx[4][2][PROD ? 1 : 32];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w  = blockIdx.x * 4 + wl;
+  if (w >= nlong) return;
+  const int r = rows[w], lo = ii[r], hi = ii[r + 1];
+  double    sum = ADD ? yin[r] : 0.0;
+  int    k  = lo + lane;
+  double a  = (k < hi) ? aa[k] : 0.0;
+  double xv = (k < hi) ? __ldg(x + aj[k]) : 0.0;
+  int    buf = 0;
+  for (int base = lo; base < hi; base += 32, buf ^= 1) {
+    if (PROD) sa[wl][buf][lane] = __dmul_rn(a, xv);
+    else { sa[wl][buf][lane] = a; sx[wl][buf][lane] = xv; }
+    __syncwarp();
+    const int kn = base + 32 + lane;          // next chunk: in flight during the chain below
+    a  = (kn < hi) ? aa[kn] : 0.0;
+    xv = (kn < hi) ? __ldg(x + aj[kn]) : 0.0;
+    if (lane == 0) {
+      const int cnt = min(32, hi - base);
+      if (cnt == 32) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) sum = PROD ? __dadd_rn(sum, sa[wl][buf][l]) : __fma_rn(sa[wl][buf][l], sx[wl][buf][l], sum);
+      } else {
+        for (int l = 0; l < cnt; ++l) sum = PROD ? __dadd_rn(sum, sa[wl][buf][l]) : __fma_rn(sa[wl][buf][l], sx[wl][buf][l], sum);
+      }
+    }
+  }
+  if (lane == 0) y[r] = sum;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -485,6 +581,10 @@ struct b200_csr_s {
   int4   *d_mtiles = nullptr, *d_msplit = nullptr;
   double *d_mhead = nullptr, *d_mtail = nullptr;
   int32_t nmtiles = 0, nmsplit = 0;
+  // exact-order merge plan: whole-row tiles + the rows longer than a tile
+  int4   *d_xtiles = nullptr;
+  int    *d_longrows = nullptr;
+  int32_t nxtiles = 0, nlong = 0;
   // vector plan
   int32_t vector_lanes = 8;
   int32_t kernel_fast = B200_KERNEL_ROW, kernel_exact = B200_KERNEL_ROW, kernel_override = 0;
@@ -677,6 +777,31 @@ static int build_idx8(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
   return B200_OK;
 }
 
+// Whole-row tiles for the exact-order merge kernel; rows longer than MERGEX_LONG are listed apart.
+static int build_mergex_plan(b200_csr_s *A, const int32_t *ai)
+{
+  const int m = A->m;
+  std::vector<int4> tiles;
+  std::vector<int>  longrows;
+  int r = 0;
+  while (r < m) {
+    // a sequential chain costs ~8 cycles per entry: rows beyond MERGEX_LONG entries get a warp of
+    // their own (64 chains per SM in flight) instead of stalling a whole CTA behind one thread
+    if (ai[r + 1] - ai[r] > MERGEX_LONG) { longrows.push_back(r); ++r; continue; }
+    int rr = r;
+    while (rr < m && ai[rr + 1] - ai[r] <= MERGE_CAP && (rr - r) < MERGE_RCAP && ai[rr + 1] - ai[rr] <= MERGEX_LONG) ++rr;
+    tiles.push_back(make_int4(r, rr, ai[r], ai[rr]));
+    r = rr;
+  }
+  A->nxtiles = (int)tiles.size();
+  A->nlong   = (int)longrows.size();
+  B200_TRY(dev_alloc(&A->d_xtiles, tiles.size(), A));
+  B200_TRY(dev_alloc(&A->d_longrows, longrows.size(), A));
+  if (!tiles.empty()) B200_CUDA_TRY(cudaMemcpy(A->d_xtiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if (!longrows.empty()) B200_CUDA_TRY(cudaMemcpy(A->d_longrows, longrows.data(), longrows.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
 // Build the plan from the host row-pointer array.
 static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
 {
@@ -803,6 +928,11 @@ static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
     // skewed row lengths: nnz-balanced merge tiles
     B200_TRY(build_merge_plan(A, ai));
     A->kernel_fast = A->nmtiles ? B200_KERNEL_MERGE : B200_KERNEL_VECTOR;
+    // the same matrices in EXACT mode: whole-row tiles summed in CSR order (+ a warp per very long row)
+    if (!A->cprow_use && !(A->ntiles && regular)) {
+      B200_TRY(build_mergex_plan(A, ai));
+      if (A->nxtiles || A->nlong) A->kernel_exact = B200_KERNEL_MERGE;
+    }
   } else A->kernel_fast = B200_KERNEL_ROW;
   return B200_OK;
 }
@@ -952,6 +1082,7 @@ extern "C" int b200_csr_destroy(b200_csr_t A)
   cudaFree(A->d_cpi); cudaFree(A->d_ridx); cudaFree(A->d_tiles);
   cudaFree(A->d_aj8); cudaFree(A->d_offs);
   cudaFree(A->d_mtiles); cudaFree(A->d_msplit); cudaFree(A->d_mhead); cudaFree(A->d_mtail);
+  cudaFree(A->d_xtiles); cudaFree(A->d_longrows);
   cudaFree(A->d_hx); cudaFree(A->d_hy);
   for (auto &s : A->hs) if (s) cudaStreamDestroy(s);
   for (auto &e : A->hev) if (e) cudaEventDestroy(e);
@@ -1105,7 +1236,22 @@ static int spmv_dispatch(b200_csr_s *A, const double *x, const double *yin, doub
   if (A->m == 0) return B200_OK;
   int kernel = A->kernel_override;
   if (!kernel) kernel = (mode == B200_MODE_FAST) ? A->kernel_fast : A->kernel_exact;
-  if (mode != B200_MODE_FAST && (kernel == B200_KERNEL_VECTOR || kernel == B200_KERNEL_MERGE))
+  // Skewed matrices: the exact-order kernels (whole-row tiles + a warp per long row) are also the
+  // fastest measured (configs[4]: 1.08 ms vs 1.23 ms for the split-row merge), so FAST uses them too;
+  // B200_MERGE_SPLIT=1 keeps the split-row merge kernel reachable for comparison.
+  const bool have_exact_plan = A->nxtiles || A->nlong;
+  if (kernel == B200_KERNEL_MERGE && (mode != B200_MODE_FAST || (have_exact_plan && !env_int("B200_MERGE_SPLIT", 0)))) {
+    if (!have_exact_plan) return set_error(B200_ERR_ARG, "no exact-order merge plan for this matrix");
+#define B200_MERGEX(MODE_)                                                                                   \
+    do {                                                                                                     \
+      if (A->nxtiles) B200_LAUNCH((k_mergex<MODE_, ADD>), A->nxtiles, MERGE_THREADS, 0, st, A->d_xtiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y); \
+      if (A->nlong) B200_LAUNCH((k_longrow<MODE_, ADD>), (A->nlong + 3) / 4, 128, 0, st, A->nlong, A->d_longrows, A->d_ai, A->d_aj, A->d_aa, x, yin, y); \
+    } while (0)
+    if (mode == B200_MODE_EXACT_FMA) B200_MERGEX(B200_MODE_EXACT_FMA); else B200_MERGEX(B200_MODE_EXACT);
+#undef B200_MERGEX
+    return B200_OK;
+  }
+  if (mode != B200_MODE_FAST && kernel == B200_KERNEL_VECTOR)
     return set_error(B200_ERR_ARG, "kernel %d cannot honour an EXACT summation order", kernel);
   if (kernel == B200_KERNEL_VECTOR) return launch_vector<ADD>(A, x, yin, y, st);
   if (kernel == B200_KERNEL_MERGE) {

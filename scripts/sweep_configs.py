@@ -32,6 +32,7 @@ def run(name, ai, aj, aa, n, transpose=False):
           f"tiles={info.stream_tiles} mtiles={info.merge_tiles} algorithmic bytes={nbytes}", flush=True)
     ref = None
     for kname, k, mode in (("auto-fast", pk.KERNEL_AUTO, pk.MODE_FAST), ("auto-exact", pk.KERNEL_AUTO, pk.MODE_EXACT),
+                           ("auto-exfma", pk.KERNEL_AUTO, pk.MODE_EXACT_FMA),
                            ("row", pk.KERNEL_ROW, pk.MODE_EXACT_FMA), ("vector", pk.KERNEL_VECTOR, pk.MODE_FAST),
                            ("stream", pk.KERNEL_STREAM, pk.MODE_EXACT_FMA), ("merge", pk.KERNEL_MERGE, pk.MODE_FAST)):
         try:

@@ -5,6 +5,8 @@ Bars (north star):
   * FAST mode: |y - y_ref| <= 1e-13 * sum_j |a_ij x_j| per row;
   * integer work (plans, compressed-row index) bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -102,6 +104,11 @@ def test_fast_mode_within_row_bound(pk, cuda, name):
         y = _run(pk, cuda, A, x, pk.MODE_FAST, kernel=k)
         assert np.all(np.abs(y - ref) <= bound), f"{name} kernel={k}: {np.max(np.abs(y - ref) - bound)}"
     if info.nz:
+        # the split-row merge kernel stays covered even where FAST now prefers the exact-order kernels
+        os.environ["B200_MERGE_SPLIT"] = "1"
+        ys = _run(pk, cuda, A, x, pk.MODE_FAST, kernel=pk.KERNEL_MERGE)
+        os.environ.pop("B200_MERGE_SPLIT")
+        assert np.all(np.abs(ys - ref) <= bound), f"{name} split-row merge"
         # merge path: deterministic from run to run (no atomics), also for MatMultAdd
         y1 = _run(pk, cuda, A, x, pk.MODE_FAST, kernel=pk.KERNEL_MERGE)
         y2 = _run(pk, cuda, A, x, pk.MODE_FAST, kernel=pk.KERNEL_MERGE)
@@ -122,6 +129,7 @@ def test_plan_picks_kernel_from_histogram(pk, cuda):
     A = pk.Csr(ai, aj, aa)
     i = A.info()
     assert pk.KERNEL_NAMES[i.kernel_fast] == "merge" and i.merge_tiles > 0
+    assert pk.KERNEL_NAMES[i.kernel_exact] == "merge"     # exact order at merge speed (whole-row tiles)
     assert sum(i.hist) == 30000
     A.destroy()
     rng = np.random.default_rng(0)
