@@ -29,6 +29,9 @@
 #include <thread>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "b200_common.h"
 
 namespace b200 {
@@ -546,6 +549,30 @@ __global__ void __launch_bounds__(256) k_tr_atomic(int m, const int *__restrict_
   for (int k = lo + lane; k < hi; k += LANES) atomicAdd(y + aj[k], alpha * aa[k]);
 }
 
+// ---- device-side transpose build (setup, once per matrix) ------------------------------------
+// row id of every non-zero (thread per row), column histogram, and the gather through the sorted
+// permutation; the stable radix sort by column keeps ascending row order inside each column.
+__global__ void k_tr_expand(int m, const int *__restrict__ ii, int *__restrict__ rowid, const int *__restrict__ aj, int *cnt)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  for (int k = ii[i]; k < ii[i + 1]; ++k) { rowid[k] = i; atomicAdd(cnt + aj[k], 1); }
+}
+__global__ void k_tr_gather(int nz, const int *__restrict__ perm, const int *__restrict__ rowid, const double *__restrict__ aa,
+                            int *__restrict__ tj, double *__restrict__ ta)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nz) return;
+  const int k = perm[p];
+  tj[p] = rowid[k];
+  ta[p] = aa[k];
+}
+__global__ void k_iota(int n, int *a)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+
 __global__ void k_copy(double *__restrict__ dst, const double *__restrict__ src, long long n)
 {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1059,7 +1086,14 @@ extern "C" int b200_csr_create_from_device(b200_csr_t *out, int32_t m, int32_t n
       B200_CUDA_TRY(cudaMemcpy(A->d_aj, d_aj, (size_t)nz * sizeof(int), cudaMemcpyDeviceToDevice));
       B200_CUDA_TRY(cudaMemcpy(A->d_aa, d_aa, (size_t)nz * sizeof(double), cudaMemcpyDeviceToDevice));
     }
-    return create_common(A, h_ai.data(), nullptr);
+    // the column indices come to the host once: the diagonal-code detection and the host-vector
+    // pipeline blocks are host work (a transpose built on the device gets the same plan as a matrix
+    // created from host arrays)
+    std::vector<int32_t> h_aj((size_t)nz);
+    if (nz) B200_CUDA_TRY(cudaMemcpy(h_aj.data(), d_aj, (size_t)nz * sizeof(int), cudaMemcpyDeviceToHost));
+    B200_TRY(create_common(A, h_ai.data(), nz ? h_aj.data() : nullptr));
+    if (A->ntiles && nz) build_host_blocks(A, h_ai.data(), h_aj.data(), A->h_tiles);
+    return B200_OK;
   }();
   if (rc) { b200_csr_destroy(A); return rc; }
   *out = A;
@@ -1334,11 +1368,62 @@ extern "C" int b200_spmv_jacobi_sweep(b200_csr_t A, const double *d_x, const dou
 // transpose: explicit copy (deterministic, ascending-row order per column = the reference's
 // scatter order) or atomics.
 // ---------------------------------------------------------------------------------------------
+// Device build: histogram of the columns -> exclusive scan = row pointers of A^T; stable radix sort
+// of the non-zero positions by column = the permutation; gather rows and values through it.
+static int build_transpose_device(b200_csr_s *A, b200_csr_t *out)
+{
+  const int m = A->m, n = A->n, nz = A->nz;
+  int    *rowid = nullptr, *cnt = nullptr, *ti = nullptr, *keys_out = nullptr, *perm_in = nullptr, *perm = nullptr, *tj = nullptr;
+  double *ta = nullptr;
+  void   *tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(rowid); cudaFree(cnt); cudaFree(ti); cudaFree(keys_out); cudaFree(perm_in); cudaFree(perm); cudaFree(tj); cudaFree(ta); cudaFree(tmp); };
+  auto body = [&]() -> int {
+    const size_t z = std::max(nz, 1);
+    B200_CUDA_TRY(cudaMalloc((void **)&rowid, z * sizeof(int)));
+    B200_CUDA_TRY(cudaMalloc((void **)&cnt, ((size_t)n + 1) * sizeof(int)));
+    B200_CUDA_TRY(cudaMalloc((void **)&ti, ((size_t)n + 1) * sizeof(int)));
+    B200_CUDA_TRY(cudaMalloc((void **)&keys_out, z * sizeof(int)));
+    B200_CUDA_TRY(cudaMalloc((void **)&perm_in, z * sizeof(int)));
+    B200_CUDA_TRY(cudaMalloc((void **)&perm, z * sizeof(int)));
+    B200_CUDA_TRY(cudaMalloc((void **)&tj, z * sizeof(int)));
+    B200_CUDA_TRY(cudaMalloc((void **)&ta, z * sizeof(double)));
+    B200_CUDA_TRY(cudaMemset(cnt, 0, ((size_t)n + 1) * sizeof(int)));
+    if (m) B200_LAUNCH(k_tr_expand, (m + 127) / 128, 128, 0, 0, m, A->d_ai, rowid, A->d_aj, cnt);
+    size_t bytes = 0;
+    B200_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, ti, n + 1));
+    B200_CUDA_TRY(cudaMalloc(&tmp, std::max<size_t>(bytes, 1)));
+    B200_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, bytes, cnt, ti, n + 1));
+    g_launches.fetch_add(1);
+    cudaFree(tmp); tmp = nullptr;
+    if (nz) {
+      B200_LAUNCH(k_iota, (nz + 255) / 256, 256, 0, 0, nz, perm_in);
+      int bits = 1;
+      while (bits < 31 && (1 << bits) < std::max(n, 2)) ++bits;
+      B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, A->d_aj, keys_out, perm_in, perm, nz, 0, bits));
+      B200_CUDA_TRY(cudaMalloc(&tmp, std::max<size_t>(bytes, 1)));
+      B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, bytes, A->d_aj, keys_out, perm_in, perm, nz, 0, bits));
+      g_launches.fetch_add(1);
+      B200_LAUNCH(k_tr_gather, (nz + 255) / 256, 256, 0, 0, nz, perm, rowid, A->d_aa, tj, ta);
+    }
+    B200_CUDA_TRY(cudaDeviceSynchronize());
+    return b200_csr_create_from_device(out, n, m, ti, tj, ta);
+  };
+  const int rc = body();
+  cleanup();
+  return rc;
+}
+
 extern "C" int b200_csr_build_transpose(b200_csr_t A)
 {
   NvtxRange nvtx_("b200_csr_build_transpose");
   if (!A) return set_error(B200_ERR_ARG, "null handle");
   if (A->T) return B200_OK;
+  if (!env_int("B200_TRANSPOSE_HOST", 0)) {
+    b200_csr_t T = nullptr;
+    B200_TRY(build_transpose_device(A, &T));
+    A->T = T;
+    return B200_OK;
+  }
   const int m = A->m, n = A->n, nz = A->nz;
   std::vector<int>    ai((size_t)m + 1), aj((size_t)nz), ti((size_t)n + 1, 0), tj((size_t)nz);
   std::vector<double> aa((size_t)nz), ta((size_t)nz);
