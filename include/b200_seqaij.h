@@ -46,8 +46,10 @@ enum {
  *   EXACT      one accumulator per row, left to right, multiply and add rounded separately
  *              (bit-exact against the oracle built with -ffp-contract=off);
  *   EXACT_FMA  same order with a fused multiply-add (bit-exact against the oracle's *_fma);
- *   FAST       kernel picked from the row-length histogram; rows may be summed by several lanes
- *              (|y - y_ref| <= 1e-13 * sum_j |a_ij x_j| per row).                              */
+ *   FAST       no order promised (|y - y_ref| <= 1e-13 * sum_j |a_ij x_j| per row).  With the
+ *              default plans FAST runs the same one-accumulator-per-row kernels as EXACT_FMA /
+ *              EXACT -- they are also the fastest measured -- so it is bit-reproducible too; only
+ *              the VECTOR / split-row MERGE overrides sum a row with several lanes.            */
 enum { B200_MODE_FAST = 0, B200_MODE_EXACT = 1, B200_MODE_EXACT_FMA = 2 };
 
 /* Kernel override for tests and sweeps (AUTO = choose from the histogram). */
@@ -56,7 +58,8 @@ enum {
   B200_KERNEL_ROW    = 1,  /* thread per row straight from global memory (the reference's shape) */
   B200_KERNEL_STREAM = 2,  /* TMA-bulk-staged CSR tiles, thread per row out of shared memory     */
   B200_KERNEL_VECTOR = 3,  /* sub-warp per row, __shfl_xor reduction                             */
-  B200_KERNEL_MERGE  = 4,  /* nnz-balanced merge-path tiles with carry fix-up                    */
+  B200_KERNEL_MERGE  = 4,  /* skewed rows: nnz-balanced whole-row tiles + a warp per long row (exact
+                              order); B200_MERGE_SPLIT=1: split-row tiles with carry fix-up       */
   B200_KERNEL_CPROW  = 5   /* compressed-row: only the non-empty rows                            */
 };
 
