@@ -384,6 +384,9 @@ extern "C" int b200_mpiaij_open_peer_window(b200_mpiaij_t M, int32_t peer, const
   if (!M || !handle64) return set_error(B200_ERR_ARG, "null argument");
   for (auto &s : M->sends)
     if (s.peer == peer) {
+      if (s.peer_window) continue;  // already mapped
+      // an IPC handle may be opened once per process: reuse a mapping made for the all-reduce
+      if (!M->all_windows.empty() && M->all_windows[peer]) { s.peer_window = M->all_windows[peer]; s.opened = false; continue; }
       cudaIpcMemHandle_t h;
       memcpy(&h, handle64, 64);
       void *p = nullptr;
