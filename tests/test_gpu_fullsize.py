@@ -137,3 +137,47 @@ def test_powerlaw_1m_merge_and_transpose(pk, cuda):
     A.mult_transpose(dx, dy, pk.MODE_EXACT)
     assert np.array_equal(dy.cpu().numpy(), oracle.matmulttranspose(ai, aj, aa, x, m))
     A.destroy()
+
+
+def test_stencil27_200_cubed_bit_exact(pk, cuda):
+    """BASELINE configs[3] at full size: 8,000,000 rows, (3*200-2)^3 = 213,847,192 non-zeros."""
+    torch = cuda
+    ai, aj, aa = gen.stencil27(200)
+    m = len(ai) - 1
+    assert (m, len(aj)) == (8_000_000, 213_847_192)
+    A = pk.Csr(ai, aj, aa)
+    assert pk.KERNEL_NAMES[A.info().kernel_exact] == "stream" and A.info().index8_diagonals == 27
+    x = pk.gen_vector(m, 0xB200)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.empty(m, dtype=torch.float64, device="cuda")
+    ref = oracle.matmult(ai, aj, aa, x)
+    A.mult(dx, dy, pk.MODE_EXACT)
+    assert np.array_equal(dy.cpu().numpy(), ref)
+    A.mult(dx, dy, pk.MODE_EXACT_FMA)
+    assert np.array_equal(dy.cpu().numpy(), oracle.matmult(ai, aj, aa, x, fma=True))
+    # box stencil: off-diagonals -1, diagonal = number of neighbours -> every row sums to zero
+    A.mult(torch.ones(m, dtype=torch.float64, device="cuda"), dy, pk.MODE_EXACT)
+    assert float(dy.abs().max()) == 0.0
+    A.destroy()
+
+
+def test_powerlaw_10m_bit_exact(pk, cuda):
+    """BASELINE configs[4] at full size: 10 M rows, lengths 1..10,000, MatMult and MatMultTranspose."""
+    torch = cuda
+    ai, aj, aa = pk.gen_powerlaw(10_000_000)
+    m = len(ai) - 1
+    lens = np.diff(ai)
+    assert lens.min() >= 1 and lens.max() == 10_000 and 9.0 < lens.mean() < 10.5
+    A = pk.Csr(ai, aj, aa)
+    assert pk.KERNEL_NAMES[A.info().kernel_exact] == "merge"
+    x = pk.gen_vector(m, 3)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.empty(m, dtype=torch.float64, device="cuda")
+    ref = oracle.matmult(ai, aj, aa, x)
+    A.mult(dx, dy, pk.MODE_EXACT)
+    assert np.array_equal(dy.cpu().numpy(), ref)
+    A.mult(dx, dy, pk.MODE_FAST)
+    assert np.all(np.abs(dy.cpu().numpy() - ref) <= 1e-13 * oracle.row_abs_sum(ai, aj, aa, x))
+    A.mult_transpose(dx, dy, pk.MODE_EXACT)
+    assert np.array_equal(dy.cpu().numpy(), oracle.matmulttranspose(ai, aj, aa, x, m))
+    A.destroy()
