@@ -56,3 +56,22 @@ def test_argument_errors_do_not_abort(pk):
     assert pk.lib.b200_spmv(None, None, None, 0, None) == 60
     assert pk.lib.b200_csr_destroy(None) == 0
     assert b"b200" in pk.lib.b200_version()
+
+
+def test_headers_are_plain_c_and_c_example_refuses_without_gpu():
+    """include/*.h compile as C99 (-pedantic); the C example links against the library and, on a
+    machine without a GPU, stops with the library's error instead of computing on the CPU."""
+    import subprocess
+    import torch
+    for h in ("b200_seqaij.h", "b200_mpiaij.h", "b200_petsc_symbols.h"):
+        src = f'#include "{h}"\nint main(void) {{ return 0; }}\n'
+        r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                            "-x", "c", "-"], input=src, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    exe = os.path.join(ROOT, "petsc-openacc_b200", "bin", "spmv_from_c")
+    assert os.path.exists(exe), "make -C petsc-openacc_b200/host builds the C example"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr

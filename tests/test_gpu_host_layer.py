@@ -144,3 +144,10 @@ def test_reference_own_driver_runs_on_the_shim(cuda):
     r = _run_driver("ref_main_ksp", n)
     ours = _run_driver("ksp_poisson", n)
     assert r["its"] == ours["its"] and r["linf"] == ours["linf"] and r["res"] == ours["res"]
+
+
+def test_c_example_runs_on_the_gpu(cuda):
+    """examples/spmv_from_c.c: the ABI from plain C99, bit-exact against the C loop it contains."""
+    exe = os.path.join(hostlib.BIN, "spmv_from_c")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "mismatches 0" in out.stdout, out.stdout + out.stderr
