@@ -53,8 +53,21 @@ def mpi_case(N, size):
             "bases": [int(b) for b in base], "ranks": ranks}
 
 
+def synthetic_case():
+    """The synthetic workloads of SURVEY 8(d): 27-point box stencil and the power-law matrix."""
+    out = {}
+    ai, aj, aa = gen.stencil27(9)
+    out["stencil27_9"] = {"nnz": len(aj), "ai": sha(ai), "aj": sha(aj), "aa": sha(aa)}
+    ai, aj, aa = gen.powerlaw(20000, lmax=3000)
+    x = gen.uniform_pm1(20000, seed=0xB200)
+    out["powerlaw_20000_3000"] = {"nnz": len(aj), "rmax": int(np.diff(ai).max()), "ai": sha(ai), "aj": sha(aj), "aa": sha(aa),
+                                  "y": sha(oracle.matmult(ai, aj, aa, x)), "yt": sha(oracle.matmulttranspose(ai, aj, aa, x, 20000))}
+    out["x_b200_16"] = sha(gen.uniform_pm1(16, seed=0xB200))
+    return out
+
+
 def main():
-    gold = {"seq": [seq_case(N) for N in (8, 50)],
+    gold = {"seq": [seq_case(N) for N in (8, 50)], "synthetic": synthetic_case(),
             "mpi": [mpi_case(N, s) for N, s in ((12, 2), (12, 4), (12, 8), (13, 8), (10, 3))],
             "decide_300": {str(s): list(oracle.dmda_decide(300, 300, 300, s)) for s in (1, 2, 4, 8)}}
     with open(os.path.join(HERE, "poisson7.json"), "w") as f:

@@ -207,3 +207,21 @@ def test_cg_jacobi_solves_reference_problem():
     A = sp.csr_matrix((p["aa"], p["aj"], p["ai"]))
     assert np.linalg.norm(A @ x - p["rhs"]) / np.linalg.norm(p["rhs"]) < 1e-9
     assert np.abs(x - p["exact"]).max() < 0.06
+
+
+def test_golden_synthetic_workloads(pk):
+    """27-point stencil, power-law matrix and the splitmix vector: numpy definition, product
+    generator and oracle results against the committed checksums."""
+    g = GOLD["synthetic"]
+    ai, aj, aa = gen.stencil27(9)
+    assert len(aj) == g["stencil27_9"]["nnz"] == (3 * 9 - 2) ** 3
+    assert (sha(ai), sha(aj), sha(aa)) == (g["stencil27_9"]["ai"], g["stencil27_9"]["aj"], g["stencil27_9"]["aa"])
+    p = g["powerlaw_20000_3000"]
+    for src in (gen.powerlaw, pk.gen_powerlaw):
+        ai, aj, aa = src(20000, lmax=3000)
+        assert (len(aj), int(np.diff(ai).max())) == (p["nnz"], p["rmax"])
+        assert (sha(ai), sha(aj), sha(aa)) == (p["ai"], p["aj"], p["aa"])
+    x = gen.uniform_pm1(20000, seed=0xB200)
+    assert sha(oracle.matmult(ai, aj, aa, x)) == p["y"]
+    assert sha(oracle.matmulttranspose(ai, aj, aa, x, 20000)) == p["yt"]
+    assert sha(gen.uniform_pm1(16, seed=0xB200)) == g["x_b200_16"] == sha(pk.gen_vector(16, 0xB200))
