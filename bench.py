@@ -179,8 +179,14 @@ def cpu_baseline(ai, aj, aa, x, n):
         oracle.matmult_mt(ai, aj, aa, x, cores, y=y)
         reps += 1
     dt = (time.perf_counter() - t0) / reps
+    # the reference's 1-core "original" protocol (runs/single-node-scaling.pbs:56), two passes
+    t1 = time.perf_counter()
+    for _ in range(2):
+        oracle.matmult_mt(ai, aj, aa, x, 1, y=y)
+    dt1 = (time.perf_counter() - t1) / 2
     return {"value": algorithmic_bytes(nnz, m) / dt / 1e9, "unit": "GB/s", "cores": cores,
             "kind": "port", "ms_per_matmult": dt * 1e3,
+            "value_1core": algorithmic_bytes(nnz, m) / dt1 / 1e9, "ms_per_matmult_1core": dt1 * 1e3,
             "sample": f"{reps} full {n}^3 MatMults (oracle/seqaij_oracle.c orc_matmult_mt), one row block per thread"}, y
 
 
@@ -279,7 +285,8 @@ def run_ours(args):
     stream_bytes = nnz * (9 if info.index8_diagonals else 12) + m * 20
     roof = {"bound": "hbm", "achieved": nbytes / kernel_ms / 1e6, "peak": peak, "unit": "GB/s",
             "frac": nbytes / kernel_ms / 1e6 / peak, "traffic": ncu_traffic(),
-            "kernel": f"k_{kname}", "kernel_ms_median": kernel_ms, "peak_source": peak_src,
+            "kernel": f"k_{kname}", "kernel_ms_median": kernel_ms, "kernel_ms_best": float(per.min()),
+            "peak_source": peak_src,
             "frac_of_nominal_8000": nbytes / kernel_ms / 1e6 / 8000.0,
             "dram_bytes_streamed_model": stream_bytes,
             "dram_gbs_streamed_model": stream_bytes / kernel_ms / 1e6,
