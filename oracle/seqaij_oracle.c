@@ -687,3 +687,121 @@ int orc_cg_jacobi(int m, const int *ii, const int *aj, const double *aa, const d
   free(r); free(z); free(p); free(w); free(dinv);
   return conv ? it : -it;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* The multigrid preconditioner the reference's options select                                  */
+/* (configs/PETSc_SolverOptions_GAMG.info:6-20): PCMG multiplicative V-cycle [P376,             */
+/* PCMGMCycle_Private] over a given hierarchy -- level l has the operator A_l (m[l] x m[l]) and, */
+/* except on the coarsest, the prolongator P_l (m[l] x m[l+1]).  Smoother: richardson(sweeps) +  */
+/* jacobi before and after; coarse "solve": one Jacobi application (preonly + jacobi).           */
+/* Each step is the separate PETSc call, separately rounded:                                    */
+/*   first pre-smoothing step from the zero guess   x = dinv .* b      (VecPointwiseMult)        */
+/*   residual                                       r = b - A x        (MatMult, VecAYPX)        */
+/*   restriction                                    b_c = P^T r        (MatMultTranspose)        */
+/*   interpolation                                  x = x + P x_c      (MatMultAdd)              */
+/*   smoothing                                      orc_jacobi_sweep                             */
+/* PCGAMG itself (the hierarchy) has no text in the reference; oracle/gamg.py restates it.       */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int            nlev, sweeps;
+  const int     *m;
+  int *const    *ai, *const *aj, *const *pi, *const *pj;
+  double *const *aa, *const *pa;
+  double       **dinv;
+} orc_mg_t;
+
+static void orc_mg_cycle(const orc_mg_t *g, int l, const double *b, double *x)
+{
+  const int     m = g->m[l];
+  const double *dinv = g->dinv[l];
+  if (l == g->nlev - 1) {
+    for (int i = 0; i < m; i++) x[i] = b[i] * dinv[i];
+    return;
+  }
+  const int mc = g->m[l + 1];
+  double   *t = malloc(sizeof(double) * (m > 0 ? m : 1)), *r = malloc(sizeof(double) * (m > 0 ? m : 1));
+  double   *bc = malloc(sizeof(double) * (mc > 0 ? mc : 1)), *xc = malloc(sizeof(double) * (mc > 0 ? mc : 1));
+  for (int i = 0; i < m; i++) x[i] = b[i] * dinv[i];
+  for (int s = 1; s < g->sweeps; s++) {
+    orc_jacobi_sweep(m, g->ai[l], g->aj[l], g->aa[l], x, b, dinv, t);
+    memcpy(x, t, sizeof(double) * m);
+  }
+  orc_residual(m, g->ai[l], g->aj[l], g->aa[l], x, b, r);
+  orc_matmulttranspose(m, mc, g->pi[l], g->pj[l], g->pa[l], r, bc);
+  orc_mg_cycle(g, l + 1, bc, xc);
+  orc_matmultadd(m, g->pi[l], g->pj[l], g->pa[l], xc, x, x);
+  for (int s = 0; s < g->sweeps; s++) {
+    orc_jacobi_sweep(m, g->ai[l], g->aj[l], g->aa[l], x, b, dinv, t);
+    memcpy(x, t, sizeof(double) * m);
+  }
+  free(t); free(r); free(bc); free(xc);
+}
+
+static void orc_mg_init(orc_mg_t *g, int nlev, int sweeps, const int *m, int *const *ai, int *const *aj,
+                        double *const *aa, int *const *pi, int *const *pj, double *const *pa)
+{
+  g->nlev = nlev; g->sweeps = sweeps; g->m = m;
+  g->ai = ai; g->aj = aj; g->aa = aa; g->pi = pi; g->pj = pj; g->pa = pa;
+  g->dinv = malloc(sizeof(double *) * nlev);
+  for (int l = 0; l < nlev; l++) {  /* PCSetUp_Jacobi [P376]: 1/diagonal, zero -> 1 */
+    g->dinv[l] = malloc(sizeof(double) * (m[l] > 0 ? m[l] : 1));
+    for (int i = 0; i < m[l]; i++) {
+      double d = 0.0;
+      for (int k = ai[l][i]; k < ai[l][i + 1]; k++) if (aj[l][k] == i) { d = aa[l][k]; break; }
+      g->dinv[l][i] = (d != 0.0) ? 1.0 / d : 1.0;
+    }
+  }
+}
+static void orc_mg_free(orc_mg_t *g)
+{
+  for (int l = 0; l < g->nlev; l++) free(g->dinv[l]);
+  free(g->dinv);
+}
+
+/* z = M^{-1} r: one V-cycle */
+void orc_mg_apply(int nlev, int sweeps, const int *m, int *const *ai, int *const *aj, double *const *aa,
+                  int *const *pi, int *const *pj, double *const *pa, const double *r, double *z)
+{
+  orc_mg_t g;
+  orc_mg_init(&g, nlev, sweeps, m, ai, aj, aa, pi, pj, pa);
+  orc_mg_cycle(&g, 0, r, z);
+  orc_mg_free(&g);
+}
+
+/* KSPSolve_CG [P376] preconditioned by the V-cycle; same conventions as orc_cg_jacobi. */
+int orc_cg_mg(int nlev, int sweeps, const int *m, int *const *ai, int *const *aj, double *const *aa,
+              int *const *pi, int *const *pj, double *const *pa, const double *b, double *x,
+              double rtol, double atol, int max_it, double *rnorm_out)
+{
+  orc_mg_t g;
+  orc_mg_init(&g, nlev, sweeps, m, ai, aj, aa, pi, pj, pa);
+  const int n = m[0];
+  double *r = malloc(sizeof(double) * n), *z = malloc(sizeof(double) * n);
+  double *p = malloc(sizeof(double) * n), *w = malloc(sizeof(double) * n);
+  memset(x, 0, sizeof(double) * n);
+  memcpy(r, b, sizeof(double) * n);
+  orc_mg_cycle(&g, 0, r, z);
+  double dp = orc_vecnorm2(n, z), rnorm0 = dp, beta = 0.0, betaold = 1.0;
+  double ttol = rtol * rnorm0 > atol ? rtol * rnorm0 : atol;
+  int    it = 0, conv = (dp < ttol);
+  beta = orc_vecdot(n, z, r);
+  while (!conv && it < max_it) {
+    if (it == 0) memcpy(p, z, sizeof(double) * n);
+    else orc_vecaypx(n, beta / betaold, z, p);
+    betaold = beta;
+    orc_matmult(n, ai[0], aj[0], aa[0], p, w);
+    double dpi = orc_vecdot(n, p, w);
+    double a   = beta / dpi;
+    orc_vecaxpy(n, a, p, x);
+    orc_vecaxpy(n, -a, w, r);
+    orc_mg_cycle(&g, 0, r, z);
+    dp = orc_vecnorm2(n, z);
+    it++;
+    if (dp < ttol) { conv = 1; break; }
+    beta = orc_vecdot(n, z, r);
+  }
+  *rnorm_out = dp;
+  free(r); free(z); free(p); free(w);
+  orc_mg_free(&g);
+  return conv ? it : -it;
+}

@@ -11,8 +11,8 @@
  *
  * Deliberate differences from PETSc: single process (MPI_* are stubs, PETSC_COMM_WORLD has one
  * rank; the multi-GPU path is include/b200_mpiaij.h driven by torch.distributed); Vec keeps a
- * device mirror with lazy host<->device sync; only KSPCG with PCJACOBI/PCNONE is implemented
- * (GAMG is outside the hot-path scope).
+ * device mirror with lazy host<->device sync; KSPCG only, with PCJACOBI, PCNONE or a PCGAMG that
+ * covers the combination the reference's options file selects (src/pcgamg.cpp).
  */
 #ifndef B200_PETSC_H
 #define B200_PETSC_H
@@ -147,6 +147,8 @@ PetscErrorCode MatCreateVecs(Mat A, Vec *right, Vec *left);
 PetscErrorCode MatZeroRowsColumns(Mat A, PetscInt n, const PetscInt rows[], PetscScalar diag, Vec x, Vec b);
 PetscErrorCode MatScale(Mat A, PetscScalar a);
 PetscErrorCode MatDestroy(Mat *A);
+/* assembled matrix from a finished CSR with ascending columns (arrays are copied) */
+PetscErrorCode MatCreateSeqAIJFromCSRB200(PetscInt m, PetscInt n, const PetscInt i[], const PetscInt j[], const PetscScalar a[], Mat *A);
 /* read access to the assembled CSR (PETSc: MatSeqAIJGetArray / MatGetRowIJ) for tests */
 PetscErrorCode MatSeqAIJGetCSRB200(Mat A, PetscInt *m, PetscInt *n, PetscInt *nz, const PetscInt **i, const PetscInt **j, const PetscScalar **a);
 PetscErrorCode MatSeqAIJGetInfoB200(Mat A, PetscInt *nonzerorowcnt, PetscInt *rmax, PetscBool *compressedrow, PetscInt *cprow_nrows, PetscInt *fshift);
@@ -193,14 +195,14 @@ PetscErrorCode DMDAVecGetArray(DM, Vec, void *array);
 PetscErrorCode DMDAVecRestoreArray(DM, Vec, void *array);
 PetscErrorCode DMDestroy(DM *);
 
-/* ---- KSP (KSPCG + PCJACOBI / PCNONE) ------------------------------------------------------- */
+/* ---- KSP (KSPCG + PCJACOBI / PCNONE / PCGAMG) ---------------------------------------------- */
 typedef struct _p_KSP *KSP;
 typedef const char    *KSPType;
 #define KSPCG "cg"
 typedef enum {
   KSP_CONVERGED_RTOL_NORMAL = 1, KSP_CONVERGED_ATOL_NORMAL = 9, KSP_CONVERGED_RTOL = 2, KSP_CONVERGED_ATOL = 3,
   KSP_CONVERGED_ITS = 4, KSP_DIVERGED_NULL = -2, KSP_DIVERGED_ITS = -3, KSP_DIVERGED_DTOL = -4,
-  KSP_DIVERGED_BREAKDOWN = -5, KSP_DIVERGED_NANORINF = -9, KSP_DIVERGED_INDEFINITE_MAT = -10,
+  KSP_DIVERGED_BREAKDOWN = -5, KSP_DIVERGED_INDEFINITE_PC = -8, KSP_DIVERGED_NANORINF = -9, KSP_DIVERGED_INDEFINITE_MAT = -10,
   KSP_CONVERGED_ITERATING = 0
 } KSPConvergedReason;
 
@@ -216,6 +218,13 @@ PetscErrorCode KSPGetConvergedReason(KSP, KSPConvergedReason *);
 PetscErrorCode KSPGetIterationNumber(KSP, PetscInt *);
 PetscErrorCode KSPGetResidualNorm(KSP, PetscReal *);
 PetscErrorCode KSPDestroy(KSP *);
+/* -pc_type gamg: read access to the hierarchy (level 0 = finest; P, agg are NULL on the coarsest)
+ * and the bare preconditioner application z = M^-1 r, for tests and tools */
+PetscErrorCode PCGAMGGetNumLevelsB200(KSP, PetscInt *nlevels);
+PetscErrorCode PCGAMGGetLevelB200(KSP, PetscInt level, Mat *A, Mat *P, Vec *dinv, const PetscInt **agg, PetscInt *nagg, PetscReal *emax);
+PetscErrorCode KSPApplyPCB200(KSP, Vec r, Vec z);
+/* largest eigenvalue of the symmetric tridiagonal with diagonal d[0..n-1], off-diagonal e[1..n-1] */
+PetscErrorCode b200_tridiag_emax(PetscInt n, const PetscReal d[], const PetscReal e[], PetscReal *emax);
 
 #ifdef __cplusplus
 }

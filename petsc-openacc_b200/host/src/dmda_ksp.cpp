@@ -6,14 +6,16 @@
 // at src/helper.cpp:31-36 builds.  Local (ghosted) numbering, the local-to-global map with -1 on
 // cells outside the domain, and DMDAVecGetArray's [k][j][i] view follow PETSc [P376].
 // KSP: KSPCG (KSPSolve_CG [P376]: left preconditioning, preconditioned residual norm,
-// KSPConvergedDefault) with PCJACOBI or PCNONE.  PCGAMG is outside the hot-path scope
-// (SURVEY 2.2 T5): it is replaced by PCJACOBI with a notice unless -b200_strict_pc is given.
+// KSPConvergedDefault) with PCJACOBI, PCNONE or PCGAMG (src/pcgamg.cpp); the Lanczos coefficients
+// of the CG recurrence can be recorded for the eigenvalue estimate PCGAMG needs.
+#include <cmath>
 #include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
 
 #include "b200_aij.h"
+#include "pc_impl.h"
 // (after b200_aij.h: the symbols header only forward-declares Mat/Vec when PETSc types are absent)
 #include "../../../include/b200_petsc_symbols.h"
 #include "../../../include/b200_seqaij.h"
@@ -178,7 +180,10 @@ struct _p_KSP {
   KSPConvergedReason reason = KSP_CONVERGED_ITERATING;
   std::string pc = "jacobi";  // PETSc's default for one rank is ilu; the reference always sets -pc_type
   bool fused = false, setup = false;
+  bool norm_none = false;     // KSP_NORM_NONE: no convergence test, exactly max_it iterations
   Vec dinv = NULL;
+  B200PCGamg *mg = NULL;
+  std::vector<PetscReal> *lanczos_d = NULL, *lanczos_e = NULL;  // KSPSetComputeSingularValues
 };
 
 extern "C" PetscErrorCode KSPCreate(MPI_Comm, KSP *k) { *k = new _p_KSP; return 0; }
@@ -209,18 +214,12 @@ extern "C" PetscErrorCode KSPSetFromOptions(KSP k)
   ierr = PetscOptionsGetInt(NULL, NULL, "-ksp_max_it", &k->max_it, NULL);CHKERRQ(ierr);
   ierr = PetscOptionsGetString(NULL, NULL, "-pc_type", buf, sizeof buf, &set);CHKERRQ(ierr);
   if (set) {
-    if (!strcmp(buf, "jacobi") || !strcmp(buf, "none")) k->pc = buf;
-    else {
-      PetscBool strict;
-      ierr = PetscOptionsGetString(NULL, NULL, "-b200_strict_pc", NULL, 0, &strict);CHKERRQ(ierr);
-      if (strict) SETERRQ1(PETSC_COMM_SELF, PETSC_ERR_SUP, "PC type %s is outside the hot-path scope (only jacobi, none)", buf);
-      ierr = PetscPrintf(PETSC_COMM_WORLD, "[b200] NOTICE: -pc_type %s is outside the hot-path scope (SURVEY 2.2 T5); using PCJACOBI. "
-                         "Iteration counts are NOT comparable with the reference's CG+GAMG.\n", buf);CHKERRQ(ierr);
-      k->pc = "jacobi";
-    }
+    if (!strcmp(buf, "jacobi") || !strcmp(buf, "none") || !strcmp(buf, "gamg")) k->pc = buf;
+    else SETERRQ1(PETSC_COMM_SELF, PETSC_ERR_SUP, "PC type %s is not supported (jacobi, none, gamg)", buf);
   }
   ierr = PetscOptionsGetString(NULL, NULL, "-ksp_b200_fused", NULL, 0, &set);CHKERRQ(ierr);
   k->fused = set;
+  k->setup = false;
   return 0;
 }
 extern "C" PetscErrorCode KSPSetUp(KSP k)
@@ -228,6 +227,7 @@ extern "C" PetscErrorCode KSPSetUp(KSP k)
   PetscErrorCode ierr;
   if (!k->A) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_WRONGSTATE, "KSPSetOperators first");
   if (k->setup) return 0;
+  if (k->mg) { ierr = b200_pcgamg_destroy(&k->mg);CHKERRQ(ierr); }
   if (k->pc == "jacobi") {
     // PCSetUp_Jacobi [P376]: diagonal, reciprocal, zero entries -> 1
     if (!k->dinv) { ierr = MatCreateVecs(k->P ? k->P : k->A, NULL, &k->dinv);CHKERRQ(ierr); }
@@ -238,6 +238,8 @@ extern "C" PetscErrorCode KSPSetUp(KSP k)
     ierr = VecGetArray(k->dinv, &d);CHKERRQ(ierr);
     for (PetscInt i = 0; i < n; ++i) d[i] = (d[i] != 0.0) ? 1.0 / d[i] : 1.0;
     ierr = VecRestoreArray(k->dinv, &d);CHKERRQ(ierr);
+  } else if (k->pc == "gamg") {
+    ierr = b200_pcgamg_setup(k->P ? k->P : k->A, &k->mg);CHKERRQ(ierr);
   }
   k->setup = true;
   return 0;
@@ -246,12 +248,14 @@ extern "C" PetscErrorCode KSPSetUp(KSP k)
 static PetscErrorCode pc_apply(KSP k, Vec r, Vec z)
 {
   if (k->pc == "jacobi") return VecPointwiseMult(z, r, k->dinv);
+  if (k->pc == "gamg") return b200_pcgamg_apply(k->mg, r, z);
   return VecCopy(r, z);
 }
 
 static bool converged(KSP k, PetscReal rnorm, PetscReal rnorm0, PetscInt it)
 {
   // KSPConvergedDefault [P376]
+  if (k->norm_none) return false;
   const PetscReal ttol = PetscMax(k->rtol * rnorm0, k->abstol);
   if (rnorm != rnorm) { k->reason = KSP_DIVERGED_NANORINF; return true; }
   if (rnorm < ttol) { k->reason = (rnorm < k->abstol) ? KSP_CONVERGED_ATOL : KSP_CONVERGED_RTOL; return true; }
@@ -266,7 +270,7 @@ extern "C" PetscErrorCode KSPSolve(KSP k, Vec b, Vec x)
   ierr = KSPSetUp(k);CHKERRQ(ierr);
   k->reason = KSP_CONVERGED_ITERATING;
   k->its = 0;
-  if (k->fused && k->pc == "jacobi") {
+  if (k->fused && k->pc == "jacobi" && !k->norm_none) {
     // one-library-call variant: everything (scalars included) stays on the device
     Mat_SeqAIJ *a = (Mat_SeqAIJ *)k->A->data;
     int rc = b200_petsc_ensure_resident(&k->A->spptr, k->A->rmap->n, k->A->cmap->n, a->i, a->j, a->a, (int64_t)k->A->state);
@@ -290,31 +294,46 @@ extern "C" PetscErrorCode KSPSolve(KSP k, Vec b, Vec x)
   ierr = VecSet(x, 0.0);CHKERRQ(ierr);
   ierr = VecCopy(b, r);CHKERRQ(ierr);
   ierr = pc_apply(k, r, z);CHKERRQ(ierr);
-  PetscReal dp, rnorm0;
-  PetscScalar beta = 0.0, betaold = 1.0, dpi, a;
-  ierr = VecNorm(z, NORM_2, &dp);CHKERRQ(ierr);
+  PetscReal dp = 0.0, rnorm0;
+  PetscScalar beta = 0.0, betaold = 1.0, dpi, a = 1.0;
+  if (!k->norm_none) { ierr = VecNorm(z, NORM_2, &dp);CHKERRQ(ierr); }
   rnorm0 = dp;
   k->rnorm = dp;
   PetscInt it = 0;
   if (!converged(k, dp, rnorm0, 0)) {
     ierr = VecDot(z, r, &beta);CHKERRQ(ierr);
+    PetscScalar dpiold = 0.0;
     while (it < k->max_it) {
+      PetscScalar bq = 0.0, eoff = 0.0;
+      // KSPSolve_CG's exits for a vanished or sign-changing (z,r) [P376]
+      if (beta == 0.0) { k->reason = KSP_CONVERGED_ATOL; break; }
+      if (it > 0 && beta * betaold < 0.0) { k->reason = KSP_DIVERGED_INDEFINITE_PC; break; }
       if (it == 0) { ierr = VecCopy(z, p);CHKERRQ(ierr); }
-      else { ierr = VecAYPX(p, beta / betaold, z);CHKERRQ(ierr); }
+      else {
+        bq = beta / betaold;
+        eoff = std::sqrt(std::fabs(bq)) / a;   // KSPCG's e[i] with the previous step length
+        ierr = VecAYPX(p, bq, z);CHKERRQ(ierr);
+      }
       betaold = beta;
       ierr = MatMult(k->A, p, w);CHKERRQ(ierr);          // -> A->ops->mult = MatMult_SeqAIJ
       ierr = VecDot(p, w, &dpi);CHKERRQ(ierr);
+      if (!k->norm_none && (dpi == 0.0 || (it > 0 && dpi * dpiold <= 0.0))) { k->reason = KSP_DIVERGED_INDEFINITE_MAT; break; }
+      dpiold = dpi;
       a = beta / dpi;
+      if (k->lanczos_d) {                                // KSPCG's d[i], e[i] [P376]
+        k->lanczos_e->push_back(eoff);
+        k->lanczos_d->push_back(std::sqrt(std::fabs(bq)) * eoff + 1.0 / a);
+      }
       ierr = VecAXPY(x, a, p);CHKERRQ(ierr);
       ierr = VecAXPY(r, -a, w);CHKERRQ(ierr);
       ierr = pc_apply(k, r, z);CHKERRQ(ierr);
-      ierr = VecNorm(z, NORM_2, &dp);CHKERRQ(ierr);
+      if (!k->norm_none) { ierr = VecNorm(z, NORM_2, &dp);CHKERRQ(ierr); }
       ++it;
       k->rnorm = dp;
       if (converged(k, dp, rnorm0, it)) break;
       ierr = VecDot(z, r, &beta);CHKERRQ(ierr);
     }
-    if (k->reason == KSP_CONVERGED_ITERATING) k->reason = KSP_DIVERGED_ITS;
+    if (k->reason == KSP_CONVERGED_ITERATING) k->reason = k->norm_none ? KSP_CONVERGED_ITS : KSP_DIVERGED_ITS;
   }
   k->its = it;
   ierr = VecDestroy(&r);CHKERRQ(ierr);
@@ -330,8 +349,94 @@ extern "C" PetscErrorCode KSPDestroy(KSP *k)
 {
   if (k && *k) {
     if ((*k)->dinv) VecDestroy(&(*k)->dinv);
+    if ((*k)->mg) b200_pcgamg_destroy(&(*k)->mg);
     delete *k;
     *k = NULL;
   }
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// largest eigenvalue of the symmetric tridiagonal (d, e[1..]) by Sturm-sequence bisection
+// (PETSc hands the same matrix to LAPACK's sterf in KSPComputeExtremeSingularValues_CG)
+// ---------------------------------------------------------------------------------------------
+extern "C" PetscErrorCode b200_tridiag_emax(PetscInt n, const PetscReal d[], const PetscReal e[], PetscReal *emax)
+{
+  if (n < 1) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE, "empty tridiagonal");
+  PetscReal lo = d[0], hi = d[0];
+  for (PetscInt i = 0; i < n; ++i) {
+    const PetscReal rad = (i > 0 ? std::fabs(e[i]) : 0.0) + (i + 1 < n ? std::fabs(e[i + 1]) : 0.0);
+    lo = PetscMin(lo, d[i] - rad);
+    hi = PetscMax(hi, d[i] + rad);
+  }
+  // count(x) = number of eigenvalues below x = negative pivots of T - x I
+  auto below = [&](PetscReal x) {
+    PetscInt  c = 0;
+    PetscReal q = 1.0;
+    for (PetscInt i = 0; i < n; ++i) {
+      const PetscReal off = (i > 0) ? e[i] * e[i] : 0.0;
+      q = d[i] - x - (i > 0 ? off / q : 0.0);
+      if (q == 0.0) q = 1e-300;
+      if (q < 0.0) ++c;
+    }
+    return c;
+  };
+  for (int it = 0; it < 200 && hi - lo > 4e-16 * PetscMax(std::fabs(lo), std::fabs(hi)); ++it) {
+    const PetscReal mid = 0.5 * (lo + hi);
+    if (below(mid) >= n) hi = mid; else lo = mid;
+  }
+  *emax = 0.5 * (lo + hi);
+  return 0;
+}
+
+PetscErrorCode b200_ksp_estimate_emax(Mat A, PetscInt its, PetscReal *emax)
+{
+  PetscErrorCode         ierr;
+  KSP                    e;
+  Vec                    bb, xx;
+  PetscScalar           *arr;
+  PetscInt               n;
+  std::vector<PetscReal> d, off;
+  ierr = MatCreateVecs(A, &xx, &bb);CHKERRQ(ierr);
+  ierr = VecGetLocalSize(bb, &n);CHKERRQ(ierr);
+  ierr = VecGetArray(bb, &arr);CHKERRQ(ierr);
+  if (b200_gen_vector(arr, n, 0x6A36ULL)) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_LIB, "b200_gen_vector");
+  ierr = VecRestoreArray(bb, &arr);CHKERRQ(ierr);
+  ierr = KSPCreate(PETSC_COMM_SELF, &e);CHKERRQ(ierr);
+  ierr = KSPSetOperators(e, A, A);CHKERRQ(ierr);
+  e->pc = "jacobi";
+  e->norm_none = true;
+  e->max_it = PetscMax(its, 1);
+  e->lanczos_d = &d;
+  e->lanczos_e = &off;
+  ierr = KSPSolve(e, bb, xx);CHKERRQ(ierr);
+  ierr = KSPDestroy(&e);CHKERRQ(ierr);
+  ierr = VecDestroy(&bb);CHKERRQ(ierr);
+  ierr = VecDestroy(&xx);CHKERRQ(ierr);
+  // a breakdown (dpi = 0 on a tiny operator) leaves non-finite entries: cut the recurrence there
+  PetscInt m = 0;
+  while (m < (PetscInt)d.size() && std::isfinite(d[m]) && std::isfinite(off[m])) ++m;
+  if (m < 1) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_CONV_FAILED, "eigenvalue estimate broke down in the first iteration");
+  return b200_tridiag_emax(m, d.data(), off.data(), emax);
+}
+
+// ---------------------------------------------------------------------------------------------
+// PC access for the tests: the hierarchy and the bare preconditioner application
+// ---------------------------------------------------------------------------------------------
+extern "C" PetscErrorCode PCGAMGGetNumLevelsB200(KSP k, PetscInt *n)
+{
+  if (!k->mg) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_WRONGSTATE, "KSPSetUp with -pc_type gamg first");
+  *n = b200_pcgamg_num_levels(k->mg);
+  return 0;
+}
+extern "C" PetscErrorCode PCGAMGGetLevelB200(KSP k, PetscInt level, Mat *A, Mat *P, Vec *dinv, const PetscInt **agg, PetscInt *nagg,
+                                             PetscReal *emax)
+{
+  if (!k->mg) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_WRONGSTATE, "KSPSetUp with -pc_type gamg first");
+  return b200_pcgamg_level(k->mg, level, A, P, dinv, agg, nagg, emax);
+}
+extern "C" PetscErrorCode KSPApplyPCB200(KSP k, Vec r, Vec z)
+{
+  PetscErrorCode ierr = KSPSetUp(k);CHKERRQ(ierr);
+  return pc_apply(k, r, z);
 }

@@ -668,6 +668,30 @@ static PetscErrorCode MatScale_SeqAIJ(Mat A, PetscScalar s)
   return PetscLogFlops((double)a->nz);
 }
 
+// An assembled SeqAIJ matrix from a finished CSR (copied): what MatCreateSeqAIJWithArrays gives in
+// PETSc, except that the Mat owns its arrays.  Used for the multigrid level operators.
+extern "C" PetscErrorCode MatCreateSeqAIJFromCSRB200(PetscInt m, PetscInt n, const PetscInt i[], const PetscInt j[], const PetscScalar v[], Mat *newA)
+{
+  if (m < 0 || n < 0 || !i || i[0] != 0) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE, "bad CSR");
+  std::vector<PetscInt> len((size_t)PetscMax(m, 1), 0);
+  for (PetscInt r = 0; r < m; ++r) {
+    len[r] = i[r + 1] - i[r];
+    if (len[r] < 0) SETERRQ1(PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE, "row pointers decrease at row %d", r);
+    for (PetscInt k = i[r]; k < i[r + 1]; ++k) {
+      if (j[k] < 0 || j[k] >= n) SETERRQ2(PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE, "column %d out of range in row %d", j[k], r);
+      if (k > i[r] && j[k] <= j[k - 1]) SETERRQ1(PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "columns of row %d are not strictly ascending", r);
+    }
+  }
+  PetscErrorCode ierr = MatCreateSeqAIJ(PETSC_COMM_SELF, m, n, 0, len.data(), newA);CHKERRQ(ierr);
+  Mat_SeqAIJ *a = (Mat_SeqAIJ *)(*newA)->data;
+  if (m && i[m]) {
+    memcpy(a->j, j, sizeof(PetscInt) * (size_t)i[m]);
+    memcpy(a->a, v, sizeof(MatScalar) * (size_t)i[m]);
+  }
+  for (PetscInt r = 0; r < m; ++r) a->ilen[r] = len[r];
+  return MatAssemblyEnd(*newA, MAT_FINAL_ASSEMBLY);
+}
+
 extern "C" PetscErrorCode MatSeqAIJGetCSRB200(Mat A, PetscInt *m, PetscInt *n, PetscInt *nz, const PetscInt **i, const PetscInt **j, const PetscScalar **v)
 {
   Mat_SeqAIJ *a = (Mat_SeqAIJ *)A->data;
