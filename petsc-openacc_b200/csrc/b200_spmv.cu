@@ -226,7 +226,10 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
   const size_t   aabytes = (size_t)(cap + STREAM_PAD) * 8, ajbytes = stream_aj_bytes(cap, IDX8);
 
   const int tid = threadIdx.x;
-  if (IDX8 && tid < 256) soffs[tid] = __ldg(ix.offs + tid);
+  if (IDX8) {
+    // all 256 table entries, also when the CTA has fewer than 256 threads (THREADS = 128 -> 160)
+    for (int t = tid; t < 256; t += THREADS + 32) soffs[t] = __ldg(ix.offs + t);
+  }
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);

@@ -273,6 +273,44 @@ def test_host_vector_pipeline_blocks(pk, cuda, monkeypatch, case):
     A.destroy()
 
 
+def test_byte_codes_with_more_diagonals_than_cta_threads(pk, cuda, monkeypatch):
+    """Regression (found by the multigrid levels, N=12 Galerkin operator: 218 rows, 169 diagonals):
+    a matrix with long rows gets 128 consumer threads (160-thread CTAs); every one of the up to 256
+    diagonal-table entries must still be loaded.  Codes >= 160 used to read an unset table slot."""
+    m = 230
+    rng = np.random.default_rng(7)
+    ai = np.zeros(m + 1, dtype=np.int32)
+    cols = []
+    for r in range(m):
+        c = np.sort(rng.choice(m, size=24, replace=False))   # dense-ish coarse operator: ~2m-1 > 160 diagonals
+        cols.append(c)
+        ai[r + 1] = ai[r] + len(c)
+    aj = np.concatenate(cols).astype(np.int32)
+    aa = rng.uniform(-1, 1, size=len(aj))
+    # keep it under 257 distinct diagonals: clip the band
+    keep = np.abs(aj - np.repeat(np.arange(m), 24)) <= 120
+    lens = np.add.reduceat(keep.astype(np.int32), ai[:-1])
+    ai = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    aj, aa = aj[keep], aa[keep]
+    monkeypatch.setenv("B200_STREAM_THREADS", "128")   # what the plan picks for rows this long anyway
+    A = pk.Csr(ai, aj, aa)
+    monkeypatch.delenv("B200_STREAM_THREADS")
+    info = A.info()
+    assert 160 < info.index8_diagonals <= 256, info.index8_diagonals
+    assert info.stream_tiles == 2                      # 128 rows per tile
+    assert pk.KERNEL_NAMES[info.kernel_exact] == "stream"
+    x, y0 = gen.uniform_pm1(m, 5), gen.uniform_pm1(m, 6)
+    for mode in (pk.MODE_EXACT, pk.MODE_EXACT_FMA, pk.MODE_FAST):
+        ref = oracle.matmult(ai, aj, aa, x, fma=(mode != pk.MODE_EXACT))
+        assert np.array_equal(_run(pk, cuda, A, x, mode), ref)
+    torch = cuda
+    dx, db = torch.from_numpy(x).cuda(), torch.from_numpy(y0).cuda()
+    out = torch.full((m,), float("nan"), dtype=torch.float64, device="cuda")
+    A.residual(dx, db, out, pk.MODE_EXACT)
+    assert np.array_equal(out.cpu().numpy(), oracle.residual(ai, aj, aa, x, y0))
+    A.destroy()
+
+
 def test_compressed_index_plan_and_equivalence(pk, cuda, monkeypatch):
     """Stencil matrices stream 1-byte diagonal codes; results are the same bits as with int32
     column indices, and matrices with more than 256 diagonals keep int32."""
