@@ -162,8 +162,26 @@ namespace {
 struct VecPriv { bool pinned; };
 std::map<Vec, VecPriv> g_vecpriv;
 
+// The host array appears on the first host access (zero-filled, page-locked when a device is
+// present): the work vectors of a solve live in HBM only and never pay for pinned memory.
+// Until then array == NULL with host_valid set means "all zeros".
+PetscErrorCode vec_host_alloc(Vec x)
+{
+  if (x->array) return 0;
+  const size_t bytes = sizeof(PetscScalar) * (size_t)PetscMax(x->n, 1);
+  void *p = NULL;
+  bool  pinned = false;
+  if (have_device() && b200_host_alloc(&p, bytes) == 0) pinned = true;
+  else p = malloc(bytes);
+  if (!p) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_MEM, "out of memory");
+  memset(p, 0, bytes);
+  x->array = (PetscScalar *)p;
+  g_vecpriv[x] = VecPriv{pinned};
+  return 0;
+}
 PetscErrorCode vec_to_host(Vec x)
 {
+  PetscErrorCode ierr = vec_host_alloc(x);CHKERRQ(ierr);
   if (!x->host_valid) {
     CUDA_CHK(cudaMemcpy(x->array, x->d_array, sizeof(PetscScalar) * (size_t)x->n, cudaMemcpyDeviceToHost));
     x->host_valid = PETSC_TRUE;
@@ -175,7 +193,8 @@ PetscErrorCode vec_to_device(Vec x, bool copy)
   if (!have_device()) SETERRQ(PETSC_COMM_SELF, 92, "vector arithmetic needs a B200: there is no CPU fallback");
   if (!x->d_array) CUDA_CHK(cudaMalloc((void **)&x->d_array, sizeof(PetscScalar) * (size_t)PetscMax(x->n, 1)));
   if (copy && !x->dev_valid) {
-    CUDA_CHK(cudaMemcpy(x->d_array, x->array, sizeof(PetscScalar) * (size_t)x->n, cudaMemcpyHostToDevice));
+    if (x->array) CUDA_CHK(cudaMemcpy(x->d_array, x->array, sizeof(PetscScalar) * (size_t)x->n, cudaMemcpyHostToDevice));
+    else CUDA_CHK(cudaMemset(x->d_array, 0, sizeof(PetscScalar) * (size_t)x->n));   // never touched on the host: zeros
     x->dev_valid = PETSC_TRUE;
   }
   return 0;
@@ -188,16 +207,9 @@ extern "C" PetscErrorCode VecCreateSeq(MPI_Comm, PetscInt n, Vec *v)
   Vec x = (Vec)calloc(1, sizeof(struct _p_Vec));
   if (!x) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_MEM, "out of memory");
   x->n = n;
-  void *p = NULL;
-  bool  pinned = false;
-  if (have_device() && b200_host_alloc(&p, sizeof(PetscScalar) * (size_t)PetscMax(n, 1)) == 0) pinned = true;
-  else p = malloc(sizeof(PetscScalar) * (size_t)PetscMax(n, 1));
-  if (!p) { free(x); SETERRQ(PETSC_COMM_SELF, PETSC_ERR_MEM, "out of memory"); }
-  memset(p, 0, sizeof(PetscScalar) * (size_t)PetscMax(n, 1));
-  x->array = (PetscScalar *)p;
+  x->array = NULL;
   x->host_valid = PETSC_TRUE;
   x->dev_valid = PETSC_FALSE;
-  g_vecpriv[x] = VecPriv{pinned};
   *v = x;
   return 0;
 }
@@ -207,8 +219,10 @@ extern "C" PetscErrorCode VecDestroy(Vec *v)
   if (!v || !*v) return 0;
   Vec x = *v;
   if (x->d_array) cudaFree(x->d_array);
-  if (g_vecpriv[x].pinned) b200_host_free(x->array); else free(x->array);
-  g_vecpriv.erase(x);
+  if (x->array) {
+    if (g_vecpriv[x].pinned) b200_host_free(x->array); else free(x->array);
+    g_vecpriv.erase(x);
+  }
   free(x);
   *v = NULL;
   return 0;
@@ -263,6 +277,7 @@ extern "C" PetscErrorCode VecSet(Vec x, PetscScalar alpha)
     B200_CHK(b200_vec_set(d, alpha, x->n, NULL));
     return 0;
   }
+  PetscErrorCode ierr = vec_host_alloc(x);CHKERRQ(ierr);
   for (PetscInt i = 0; i < x->n; ++i) x->array[i] = alpha;  // pure assignment, no arithmetic
   x->host_valid = PETSC_TRUE; x->dev_valid = PETSC_FALSE; x->state++;
   return 0;
@@ -277,6 +292,8 @@ extern "C" PetscErrorCode VecCopy(Vec x, Vec y)
     B200_CHK(b200_vec_copy(d, x->d_array, x->n, NULL));
     return 0;
   }
+  PetscErrorCode ierr = vec_host_alloc(x);CHKERRQ(ierr);
+  ierr = vec_host_alloc(y);CHKERRQ(ierr);
   memcpy(y->array, x->array, sizeof(PetscScalar) * (size_t)x->n);
   y->host_valid = PETSC_TRUE; y->dev_valid = PETSC_FALSE; y->state++;
   return 0;
