@@ -4,7 +4,8 @@
 // runs/single-node-scaling.pbs:60-64) and ends with the five report lines in the format
 // scripts/generate_plots.py:87-90 parses, so logs of this driver drop into the reference's plotting
 // flow.  Organised as three timed phases held in a small table instead of the reference's flat
-// main(); `-b200_json 1` adds a machine-readable line.
+// main(); `-b200_json 1` adds a machine-readable line, `-b200_solve_repeat n` runs KSPSolve n times
+// and also reports the fastest (the first one pays for allocations and first kernel launches).
 #include <petscksp.h>
 #include <petsctime.h>
 
@@ -49,6 +50,8 @@ PetscErrorCode load_options()
   return 0;
 }
 
+double g_best_solve = -1.0;
+
 PetscErrorCode report(const Problem &p, const std::vector<Phase> &phases)
 {
   PetscErrorCode     ierr;
@@ -77,8 +80,9 @@ PetscErrorCode report(const Problem &p, const std::vector<Phase> &phases)
     ierr = PetscGetFlops(&flops);CHKERRQ(ierr);
     ierr = PetscPrintf(PETSC_COMM_WORLD,
                        "{\"grid\": [%d, %d, %d], \"iterations\": %d, \"residual\": %.17g, \"error_inf\": %.17g, "
-                       "\"solve_s\": %.6f, \"flops\": %.0f}\n",
-                       info.mx, info.my, info.mz, its, rnorm, err_inf, phases[2].seconds, flops);CHKERRQ(ierr);
+                       "\"solve_s\": %.6f, \"solve_s_best\": %.6f, \"flops\": %.0f}\n",
+                       info.mx, info.my, info.mz, its, rnorm, err_inf, phases[2].seconds,
+                       g_best_solve >= 0.0 ? g_best_solve : phases[2].seconds, flops);CHKERRQ(ierr);
   }
   return 0;
 }
@@ -108,6 +112,16 @@ int main(int argc, char **argv)
                     }});
   phases.push_back({"solve", [&]() { return KSPSolve(p.solver, p.f, p.u); }});
   for (auto &ph : phases) { ierr = timed(ph);CHKERRQ(ierr); }
+  {
+    PetscInt repeat = 1;
+    ierr = PetscOptionsGetInt(nullptr, nullptr, "-b200_solve_repeat", &repeat, nullptr);CHKERRQ(ierr);
+    g_best_solve = phases[2].seconds;
+    for (PetscInt k = 1; k < repeat; ++k) {   // KSPSolve starts from the zero guess every time
+      Phase again{"solve", [&]() { return KSPSolve(p.solver, p.f, p.u); }};
+      ierr = timed(again);CHKERRQ(ierr);
+      if (again.seconds < g_best_solve) g_best_solve = again.seconds;
+    }
+  }
 
   ierr = report(p, phases);CHKERRQ(ierr);
   ierr = KSPDestroy(&p.solver);CHKERRQ(ierr);
