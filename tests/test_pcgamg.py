@@ -336,3 +336,73 @@ def test_reference_driver_runs_its_own_gamg_options(cuda, tmp_path):
     p = oracle.poisson7(20)
     _, its_j, _ = oracle.cg_jacobi(p["ai"], p["aj"], p["aa"], p["rhs"])
     assert 0 < its * 2 < its_j
+
+
+# ---- CPU: the set-up on matrices that are not the reference problem -------------------------------
+def _graph_laplacian(n, extra_edges, rng, isolated=(), weights=(0.5, 2.0), shift=0.0):
+    """Weighted graph Laplacian (+ shift I): a ring plus random chords; `isolated` vertices keep only
+    their diagonal.  Symmetric M-matrix, ascending columns."""
+    rows, cols, vals = [], [], []
+    edges = {(i, (i + 1) % n) for i in range(n)}
+    for _ in range(extra_edges):
+        a, b = rng.integers(0, n, 2)
+        if a != b:
+            edges.add((min(a, b), max(a, b)))
+    for a, b in edges:
+        if a in isolated or b in isolated:
+            continue
+        w = rng.uniform(*weights)
+        rows += [a, b]; cols += [b, a]; vals += [-w, -w]
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()
+    A.sum_duplicates()
+    d = -np.asarray(A.sum(axis=1)).ravel() + shift
+    d[list(isolated)] = 1.0
+    A = (A + sp.diags(d)).tocsr()
+    A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("seed,n,extra,threshold", [(1, 400, 300, 0.0), (2, 900, 200, 0.0), (3, 700, 1500, 0.05), (4, 300, 0, 0.0)])
+def test_setup_on_random_graph_laplacians(seed, n, extra, threshold):
+    rng = np.random.default_rng(seed)
+    isolated = tuple(int(v) for v in rng.choice(n, size=5, replace=False))
+    A = _graph_laplacian(n, extra, rng, isolated=isolated, shift=1e-3)
+    M = hostlib.mat_from_csr(A.indptr, A.indices, A.data, n)
+    sv = Solver(M, {"-pc_gamg_b200_esteig": "gershgorin", "-pc_gamg_threshold": threshold})
+    assert sv.setup_rc == 0
+    got = sv.levels()
+    want = gamg.hierarchy(A.indptr, A.indices, A.data, threshold=threshold, esteig="gershgorin")
+    assert [g["m"] for g in got] == [w["A"].shape[0] for w in want]
+    alone = np.nonzero(np.diff(A.indptr) == 1)[0]                    # diagonal-only rows join no aggregate
+    assert set(alone) >= set(isolated) and np.array_equal(np.nonzero(got[0]["agg"] < 0)[0], alone)
+    for g, w in zip(got[:-1], want[:-1]):
+        assert np.array_equal(g["agg"], w["agg"])
+        P = as_sp(g["P"], g["pn"])
+        assert abs(P - w["P"]).max() <= 1e-12 * abs(w["P"]).max()
+    for g, w in zip(got[1:], want[1:]):
+        assert abs(as_sp(g["A"]) - w["A"]).max() <= 1e-12 * abs(w["A"]).max()
+    # the restated CG + V-cycle converges on it, in fewer iterations than Jacobi-CG
+    b = gen.uniform_pm1(n, 40 + seed)
+    x, its, rn = gamg.cg_mg(got, b, rtol=1e-10, atol=1e-50)
+    assert its > 0 and np.abs(A @ x - b).max() <= 1e-6 * np.abs(b).max()
+    _, its_j, _ = oracle.cg_jacobi(A.indptr, A.indices, A.data, b, rtol=1e-10, atol=1e-50)
+    assert its <= its_j
+    sv.destroy()
+    hostlib.chk(hostlib.lib().MatDestroy(C.byref(M)))
+
+
+def test_setup_degenerate_operators():
+    """Nothing to coarsen: a diagonal matrix (every vertex isolated) and a 1x1 operator give a
+    one-level hierarchy whose "V-cycle" is the coarse Jacobi application."""
+    for A in (sp.diags(np.arange(1.0, 8.0)).tocsr(), sp.csr_matrix(np.array([[4.0]]))):
+        n = A.shape[0]
+        M = hostlib.mat_from_csr(A.indptr, A.indices, A.data, n)
+        sv = Solver(M, {"-pc_gamg_b200_esteig": "gershgorin"})
+        assert sv.setup_rc == 0
+        lv = sv.levels()
+        assert len(lv) == 1 and lv[0]["P"] is None
+        assert np.array_equal(lv[0]["dinv"], 1.0 / A.diagonal())
+        r = np.arange(1.0, n + 1.0)
+        assert np.array_equal(gamg.mg_apply(lv, r), r / A.diagonal())
+        sv.destroy()
+        hostlib.chk(hostlib.lib().MatDestroy(C.byref(M)))
