@@ -93,68 +93,105 @@ void parallel_blocks(PetscInt m, F f)
   for (auto &x : th) x.join();
 }
 
-// C = X * Y, row by row with a dense accumulator; every entry is summed over X's row in storage
-// order (then over Y's row), so the result does not depend on the thread count.
-PetscErrorCode spgemm(const CsrView &X, const CsrView &Y, Csr &C)
+// Rows of a CSR built independently: `row(t, r, j, a)` appends the entries of row r (ascending
+// columns) to the calling thread's buffers.  Row blocks run on the set-up threads; the blocks are
+// then laid end to end, so the result does not depend on the thread count.
+template <class RowFn>
+PetscErrorCode build_rows(PetscInt m, PetscInt n, bool values, Csr &C, RowFn row)
 {
-  if (X.n != Y.m) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_SIZ, "spgemm: inner dimensions differ");
-  const int nt = (X.m < 20000) ? 1 : setup_threads();
+  const int nt = (m < 20000) ? 1 : setup_threads();
   struct Part { std::vector<PetscInt> len, j; std::vector<MatScalar> a; };
   std::vector<Part> parts(nt);
-  parallel_blocks(X.m, [&](int t, PetscInt r0, PetscInt r1) {
+  parallel_blocks(m, [&](int t, PetscInt r0, PetscInt r1) {
     Part &p = parts[t];
-    std::vector<PetscInt>  mark((size_t)std::max(Y.n, 1), -1), cols;
-    std::vector<MatScalar> acc((size_t)std::max(Y.n, 1), 0.0);
-    p.len.reserve((size_t)(r1 - r0));
+    p.len.resize((size_t)(r1 - r0));
     for (PetscInt r = r0; r < r1; ++r) {
-      cols.clear();
-      for (PetscInt k = X.i[r]; k < X.i[r + 1]; ++k) {
-        const MatScalar xv = X.a[k];
-        const PetscInt  q  = X.j[k];
-        for (PetscInt l = Y.i[q]; l < Y.i[q + 1]; ++l) {
-          const PetscInt c = Y.j[l];
-          if (mark[c] != r) { mark[c] = r; cols.push_back(c); acc[c] = xv * Y.a[l]; }
-          else acc[c] += xv * Y.a[l];
-        }
-      }
-      std::sort(cols.begin(), cols.end());
-      p.len.push_back((PetscInt)cols.size());
-      for (PetscInt c : cols) { p.j.push_back(c); p.a.push_back(acc[c]); }
+      const size_t before = p.j.size();
+      row(t, r, p.j, p.a);
+      p.len[r - r0] = (PetscInt)(p.j.size() - before);
     }
   });
-  long long nz = 0;
-  for (auto &p : parts) nz += (long long)p.j.size();
-  if (nz > 2147483647LL) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE, "sparse product exceeds int32 indices");
-  C.m = X.m; C.n = Y.n;
-  C.i.assign((size_t)X.m + 1, 0);
-  C.j.resize((size_t)nz); C.a.resize((size_t)nz);
-  PetscInt row = 0;
-  size_t   pos = 0;
-  for (auto &p : parts) {
-    for (PetscInt l : p.len) { C.i[row + 1] = C.i[row] + l; ++row; }
-    std::copy(p.j.begin(), p.j.end(), C.j.begin() + pos);
-    std::copy(p.a.begin(), p.a.end(), C.a.begin() + pos);
-    pos += p.j.size();
+  std::vector<long long> first((size_t)nt + 1, 0);
+  for (int t = 0; t < nt; ++t) first[t + 1] = first[t] + (long long)parts[t].j.size();
+  if (first[nt] > 2147483647LL) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE, "sparse product exceeds int32 indices");
+  C.m = m; C.n = n;
+  C.i.assign((size_t)m + 1, 0);
+  C.j.resize((size_t)first[nt]);
+  C.a.resize(values ? (size_t)first[nt] : 0);
+  parallel_blocks(m, [&](int t, PetscInt r0, PetscInt r1) {
+    Part    &p   = parts[t];
+    PetscInt pos = (PetscInt)first[t];
+    for (PetscInt r = r0; r < r1; ++r) { C.i[r] = pos; pos += p.len[r - r0]; }
+    std::copy(p.j.begin(), p.j.end(), C.j.begin() + first[t]);
+    if (values) std::copy(p.a.begin(), p.a.end(), C.a.begin() + first[t]);
     p = Part();
-  }
+  });
+  C.i[m] = (PetscInt)first[nt];
   return 0;
 }
 
-// stable counting-sort transpose: row c of the result lists column c's entries by ascending row
+// C = X * Y, row by row with a dense accumulator; every entry is summed over X's row in storage
+// order (then over Y's row).
+PetscErrorCode spgemm(const CsrView &X, const CsrView &Y, Csr &C)
+{
+  if (X.n != Y.m) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_SIZ, "spgemm: inner dimensions differ");
+  struct Scratch { std::vector<PetscInt> mark, cols; std::vector<MatScalar> acc; };
+  std::vector<Scratch> scratch((size_t)setup_threads());
+  return build_rows(X.m, Y.n, true, C, [&](int t, PetscInt r, std::vector<PetscInt> &cj, std::vector<MatScalar> &ca) {
+    Scratch &w = scratch[t];
+    if (w.mark.empty()) { w.mark.assign((size_t)std::max(Y.n, 1), -1); w.acc.assign((size_t)std::max(Y.n, 1), 0.0); }
+    w.cols.clear();
+    for (PetscInt k = X.i[r]; k < X.i[r + 1]; ++k) {
+      const MatScalar xv = X.a[k];
+      const PetscInt  q  = X.j[k];
+      for (PetscInt l = Y.i[q]; l < Y.i[q + 1]; ++l) {
+        const PetscInt c = Y.j[l];
+        if (w.mark[c] != r) { w.mark[c] = r; w.cols.push_back(c); w.acc[c] = xv * Y.a[l]; }
+        else w.acc[c] += xv * Y.a[l];
+      }
+    }
+    std::sort(w.cols.begin(), w.cols.end());
+    for (PetscInt c : w.cols) { cj.push_back(c); ca.push_back(w.acc[c]); }
+  });
+}
+
+// transpose: row c of the result lists column c's entries by ascending row.  Row blocks count
+// their columns on the set-up threads; block t's entries of a column go after those of the blocks
+// before it, so the order (and the result) is the sequential one.
 void transpose(const CsrView &X, Csr &T)
 {
   T.m = X.n; T.n = X.m;
   const PetscInt nz = X.i[X.m];
   T.i.assign((size_t)X.n + 1, 0);
   T.j.resize((size_t)nz); T.a.resize((size_t)nz);
-  for (PetscInt k = 0; k < nz; ++k) T.i[X.j[k] + 1]++;
-  for (PetscInt c = 0; c < X.n; ++c) T.i[c + 1] += T.i[c];
-  std::vector<PetscInt> next(T.i.begin(), T.i.end() - 1);
-  for (PetscInt r = 0; r < X.m; ++r)
-    for (PetscInt k = X.i[r]; k < X.i[r + 1]; ++k) {
-      const PetscInt p = next[X.j[k]]++;
-      T.j[p] = r; T.a[p] = X.a[k];
-    }
+  int nt = (X.m < 20000) ? 1 : setup_threads();
+  while (nt > 1 && (size_t)nt * (size_t)X.n > (size_t)256 << 20) nt /= 2;   // cap the count tables at 1 GB
+  std::vector<std::vector<PetscInt>> next((size_t)nt, std::vector<PetscInt>((size_t)X.n, 0));
+  auto block = [&](int t) { return std::make_pair((PetscInt)((long long)X.m * t / nt), (PetscInt)((long long)X.m * (t + 1) / nt)); };
+  auto each = [&](auto f) {
+    if (nt == 1) { f(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(f, t);
+    for (auto &x : th) x.join();
+  };
+  each([&](int t) {
+    const auto [r0, r1] = block(t);
+    for (PetscInt k = X.i[r0]; k < X.i[r1]; ++k) next[t][X.j[k]]++;
+  });
+  PetscInt pos = 0;
+  for (PetscInt c = 0; c < X.n; ++c) {   // next[t][c] <- where block t starts writing column c
+    T.i[c] = pos;
+    for (int t = 0; t < nt; ++t) { const PetscInt cnt = next[t][c]; next[t][c] = pos; pos += cnt; }
+  }
+  T.i[X.n] = pos;
+  each([&](int t) {
+    const auto [r0, r1] = block(t);
+    for (PetscInt r = r0; r < r1; ++r)
+      for (PetscInt k = X.i[r]; k < X.i[r + 1]; ++k) {
+        const PetscInt p = next[t][X.j[k]]++;
+        T.j[p] = r; T.a[p] = X.a[k];
+      }
+  });
 }
 
 void diagonal(const CsrView &A, std::vector<MatScalar> &d)
@@ -165,21 +202,17 @@ void diagonal(const CsrView &A, std::vector<MatScalar> &d)
 }
 
 // PCGAMGGraph_AGG + PCGAMGFilterGraph [P376]: pattern of the strong off-diagonal connections
-void strength_graph(const CsrView &A, const std::vector<MatScalar> &d, PetscReal threshold, Csr &G)
+PetscErrorCode strength_graph(const CsrView &A, const std::vector<MatScalar> &d, PetscReal threshold, Csr &G)
 {
-  G.m = G.n = A.m;
-  G.i.assign((size_t)A.m + 1, 0);
-  G.j.clear(); G.a.clear();
   std::vector<PetscReal> s((size_t)A.m);
   for (PetscInt r = 0; r < A.m; ++r) s[r] = (d[r] != 0.0) ? 1.0 / std::sqrt(std::fabs(d[r])) : 1.0;
-  for (PetscInt r = 0; r < A.m; ++r) {
+  return build_rows(A.m, A.m, false, G, [&](int, PetscInt r, std::vector<PetscInt> &gj, std::vector<MatScalar> &) {
     for (PetscInt k = A.i[r]; k < A.i[r + 1]; ++k) {
       const PetscInt c = A.j[k];
       if (c == r || c >= A.m) continue;
-      if (std::fabs(A.a[k]) * s[r] * s[c] > threshold) G.j.push_back(c);
+      if (std::fabs(A.a[k]) * s[r] * s[c] > threshold) gj.push_back(c);
     }
-    G.i[r + 1] = (PetscInt)G.j.size();
-  }
+  });
 }
 
 // greedy MIS in natural order on G (square = false) or on G*G (square = true, never formed);
@@ -231,23 +264,18 @@ void tentative_prolongator(const std::vector<PetscInt> &agg, PetscInt nagg, cons
 }
 
 // P = P0 + alpha * D^-1 (A P0), alpha = -1.4 / emax (PCGAMGOptProlongator_AGG [P376])
-void smooth_prolongator(const Csr &AP0, const Csr &P0, const std::vector<MatScalar> &d, PetscReal alpha, Csr &P)
+PetscErrorCode smooth_prolongator(const Csr &AP0, const Csr &P0, const std::vector<MatScalar> &d, PetscReal alpha, Csr &P)
 {
-  P.m = P0.m; P.n = P0.n;
-  P.i.assign((size_t)P0.m + 1, 0);
-  P.j.clear(); P.a.clear();
-  P.j.reserve(AP0.j.size()); P.a.reserve(AP0.a.size());
-  for (PetscInt r = 0; r < P0.m; ++r) {
+  return build_rows(P0.m, P0.n, true, P, [&](int, PetscInt r, std::vector<PetscInt> &pj, std::vector<MatScalar> &pa) {
     const MatScalar dinv = (d[r] != 0.0) ? 1.0 / d[r] : 1.0;
     PetscInt        k = AP0.i[r], l = P0.i[r];
     const PetscInt  ke = AP0.i[r + 1], le = P0.i[r + 1];
     while (k < ke || l < le) {  // merge of two ascending rows
-      if (l >= le || (k < ke && AP0.j[k] < P0.j[l])) { P.j.push_back(AP0.j[k]); P.a.push_back(alpha * (dinv * AP0.a[k])); ++k; }
-      else if (k >= ke || P0.j[l] < AP0.j[k]) { P.j.push_back(P0.j[l]); P.a.push_back(P0.a[l]); ++l; }
-      else { P.j.push_back(P0.j[l]); P.a.push_back(P0.a[l] + alpha * (dinv * AP0.a[k])); ++k; ++l; }
+      if (l >= le || (k < ke && AP0.j[k] < P0.j[l])) { pj.push_back(AP0.j[k]); pa.push_back(alpha * (dinv * AP0.a[k])); ++k; }
+      else if (k >= ke || P0.j[l] < AP0.j[k]) { pj.push_back(P0.j[l]); pa.push_back(P0.a[l]); ++l; }
+      else { pj.push_back(P0.j[l]); pa.push_back(P0.a[l] + alpha * (dinv * AP0.a[k])); ++k; ++l; }
     }
-    P.i[r + 1] = (PetscInt)P.j.size();
-  }
+  });
 }
 
 // upper bound of lambda_max(D^-1 A) from the absolute row sums (-pc_gamg_b200_esteig gershgorin)
@@ -405,7 +433,7 @@ PetscErrorCode b200_pcgamg_setup(Mat Afine, B200PCGamg **out)
     diagonal(A, d);
     Csr G;
     sw.lap();
-    strength_graph(A, d, threshold, G);
+    ierr = strength_graph(A, d, threshold, G);CHKERRQ(ierr);
     t_graph += sw.lap();
     std::vector<PetscInt> agg;
     const PetscInt        nagg = aggregate(G, (PetscInt)l < square_graph, agg);
@@ -424,7 +452,7 @@ PetscErrorCode b200_pcgamg_setup(Mat Afine, B200PCGamg **out)
       if (!(emax > 0.0)) SETERRQ1(PETSC_COMM_SELF, PETSC_ERR_CONV_FAILED, "eigenvalue estimate %g is not positive", emax);
       Csr AP0;
       ierr = spgemm(A, P0.view(), AP0);CHKERRQ(ierr);
-      smooth_prolongator(AP0, P0, d, -1.4 / emax, P);
+      ierr = smooth_prolongator(AP0, P0, d, -1.4 / emax, P);CHKERRQ(ierr);
     } else P = std::move(P0);
     t_prol += sw.lap();
 
