@@ -13,7 +13,9 @@ One JSON line on rank 0:
   e2e       the same metric through the host-vector entry point (what MatMult_SeqAIJ(Mat,Vec,Vec)
             sees with PETSc 3.7.6 host Vecs): pinned-host x uploaded and y downloaded every step;
   roofline  achieved GB/s of the dominant kernel against MEASURED_PEAKS.json's copy bandwidth;
-  cpu_baseline  the oracle (CPU restatement of the reference kernel) on the box's host cores.
+  cpu_baseline  the reference's CPU row loop on the box's host cores: oracle/_ref (its own loop text
+            compiled from its patch files, kind "reference") when that was built, else the oracle's
+            restatement (kind "port").
 --impl reference times that CPU kernel as the arm to compare against.
 """
 import argparse
@@ -131,9 +133,19 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def cpu_kernel(oracle):
+    """(threaded MatMult, kind, description): the reference's own loop text when oracle/_ref was
+    built (ref_harness.c around the loops cut from src/openacc-step1/MatMult_SeqAIJ.patch), else
+    the oracle's restatement of it.  Same bits either way (tests/test_oracle.py)."""
+    if oracle.ref_lib() is not None:
+        return oracle.ref_matmult_mt, "reference", "oracle/_ref/libref_matmult.so ref_matmult_mt: the reference's MatMult_SeqAIJ row loop"
+    return oracle.matmult_mt, "port", "oracle/seqaij_oracle.c orc_matmult_mt"
+
+
 def run_reference(args):
-    """The reference's CPU MatMult_SeqAIJ loop (oracle restatement: PETSc cannot be built offline
-    here), one contiguous row block per host thread ~ one MPI rank per core."""
+    """The reference's CPU MatMult_SeqAIJ loop (its own text from oracle/_ref, or the oracle's
+    restatement where that is not built; PETSc as a whole cannot be built offline), one contiguous
+    row block per host thread ~ one MPI rank per core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -145,11 +157,12 @@ def run_reference(args):
     x = pk.gen_vector(m, 0xB200)
     y = np.empty(m)
     cores = host_threads()
+    matmult_mt, kind, what = cpu_kernel(oracle)
     for _ in range(max(args.warmup, 1)):
-        oracle.matmult_mt(ai, aj, aa, x, cores, y=y)
+        matmult_mt(ai, aj, aa, x, cores, y=y)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.matmult_mt(ai, aj, aa, x, cores, y=y)
+        matmult_mt(ai, aj, aa, x, cores, y=y)
     dt = (time.perf_counter() - t0) / args.steps
     gbs = algorithmic_bytes(nnz, m) / dt / 1e9
     line = {
@@ -159,8 +172,8 @@ def run_reference(args):
         "data": "synthetic", "gflops": 2.0 * nnz / dt / 1e9,
         "config": {"workload": f"3D Poisson 7-point {n}^3 fp64 MatMult_SeqAIJ, CPU host threads",
                    "rows": m, "nnz": nnz, "algorithmic_bytes": algorithmic_bytes(nnz, m)},
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full {n}^3 MatMults, one nnz-balanced row block per thread"},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} full {n}^3 MatMults ({what}), one nnz-balanced row block per thread"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -173,21 +186,22 @@ def cpu_baseline(ai, aj, aa, x, n):
     cores = host_threads()
     m, nnz = len(ai) - 1, len(aj)
     y = np.empty(m)
-    oracle.matmult_mt(ai, aj, aa, x, cores, y=y)
+    matmult_mt, kind, what = cpu_kernel(oracle)
+    matmult_mt(ai, aj, aa, x, cores, y=y)
     reps, t0 = 0, time.perf_counter()
     while reps < 10 or (time.perf_counter() - t0 < 2.0 and reps < 200):
-        oracle.matmult_mt(ai, aj, aa, x, cores, y=y)
+        matmult_mt(ai, aj, aa, x, cores, y=y)
         reps += 1
     dt = (time.perf_counter() - t0) / reps
     # the reference's 1-core "original" protocol (runs/single-node-scaling.pbs:56), two passes
     t1 = time.perf_counter()
     for _ in range(2):
-        oracle.matmult_mt(ai, aj, aa, x, 1, y=y)
+        matmult_mt(ai, aj, aa, x, 1, y=y)
     dt1 = (time.perf_counter() - t1) / 2
     return {"value": algorithmic_bytes(nnz, m) / dt / 1e9, "unit": "GB/s", "cores": cores,
-            "kind": "port", "ms_per_matmult": dt * 1e3,
+            "kind": kind, "ms_per_matmult": dt * 1e3,
             "value_1core": algorithmic_bytes(nnz, m) / dt1 / 1e9, "ms_per_matmult_1core": dt1 * 1e3,
-            "sample": f"{reps} full {n}^3 MatMults (oracle/seqaij_oracle.c orc_matmult_mt), one row block per thread"}, y
+            "sample": f"{reps} full {n}^3 MatMults ({what}), one row block per thread"}, y
 
 
 def run_ours(args):

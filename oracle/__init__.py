@@ -53,6 +53,51 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+# ---- oracle/_ref: the reference's own MatMult loops, compiled from its patch files -------------
+_REF_SO = os.path.join(_HERE, "_ref", "libref_matmult.so")
+_ref = None
+
+
+def ref_lib():
+    """CDLL of oracle/_ref/libref_matmult.so (ref_harness.c + the loop text extract_ref_loops.py cuts
+    from the reference tree at build time), or None where it was never built."""
+    global _ref
+    if _ref is None and os.path.exists(_REF_SO):
+        _ref = C.CDLL(_REF_SO)
+    return _ref
+
+
+def ref_matmult(ai, aj, aa, x, variant="original", host_rows=0):
+    """y = A x by the reference's loop text.  variant "original": PETSc 3.7.6's loop as the step-1
+    patch shows it; "step3": the author's host loop for the first `host_rows` rows, then the device
+    loop (src/openacc-step3/MatMult_SeqAIJ.patch:36-70) compiled as plain C."""
+    L = ref_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_matmult.so is not built (make -C oracle with the reference tree mounted)")
+    ai, aj, aa, x = _i32(ai), _i32(aj), _f64(aa), _f64(x)
+    m = len(ai) - 1
+    y = np.empty(m, dtype=np.float64)
+    if variant == "original":
+        L.ref_matmult_original(C.c_int(m), _p(ai), _p(aj), _p(aa), _p(x), _p(y))
+    elif variant == "step3":
+        L.ref_matmult_step3(C.c_int(m), _p(ai), _p(aj), _p(aa), _p(x), _p(y), C.c_int(host_rows))
+    else:
+        raise ValueError(variant)
+    return y
+
+
+def ref_matmult_mt(ai, aj, aa, x, nthreads, y=None):
+    """The reference's loop on `nthreads` row blocks (one MPI rank per core in its runs)."""
+    L = ref_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_matmult.so is not built")
+    m = len(ai) - 1
+    if y is None:
+        y = np.empty(m, dtype=np.float64)
+    L.ref_matmult_mt(C.c_int(nthreads), C.c_int(m), _p(ai), _p(aj), _p(aa), _p(x), _p(y))
+    return y
+
+
 # ---- SpMV family -----------------------------------------------------------------------------
 def matmult(ai, aj, aa, x, fma=False):
     ai, aj, aa, x = _i32(ai), _i32(aj), _f64(aa), _f64(x)

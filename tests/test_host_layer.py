@@ -99,3 +99,37 @@ def test_reference_driver_compiles_unmodified():
     out = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(hostlib.BIN, "ref_main_ksp")], capture_output=True, text=True).stdout
     for sym in ("KSPSolve", "MatSetValues", "DMDACreate3d", "MatZeroRowsColumns"):
         assert sym in out
+
+
+REF_HELPER = os.path.join(hostlib.ROOT, "oracle", "_ref", "libref_helper.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HELPER), reason="oracle/_ref/libref_helper.so is built only where the reference tree is mounted")
+@pytest.mark.parametrize("dims", [(5, 5, 5), (12, 12, 12), (6, 4, 9), (30, 30, 30)])
+def test_reference_own_problem_builder_gives_the_oracle_bits(dims):
+    """The reference's OWN src/helper.cpp (createSystem -> generateRHS/generateExt/generateA/
+    setRefPoint), compiled unmodified from where it lies into oracle/_ref, run on this host layer's
+    DMDA / MatSetValues / MatZeroRowsColumns: the assembled CSR, the right-hand side and the exact
+    solution are bit-identical to the oracle's restatement -- which pins both the restatement and
+    the host layer to the reference's code for row A9 of the scope table."""
+    import ctypes as C
+    hostlib.lib()   # libb200aij / libb200petsc first
+    R = C.CDLL(REF_HELPER)
+    nx, ny, nz = (C.c_int(d) for d in dims)
+    da, A, lhs, rhs, exact = (C.c_void_p(0) for _ in range(5))
+    hostlib.chk(R.createSystem(C.byref(nx), C.byref(ny), C.byref(nz), C.byref(da), C.byref(A), C.byref(lhs), C.byref(rhs),
+                               C.byref(exact)))
+    n = dims[0] * dims[1] * dims[2]
+    m, nn, nnz = C.c_int(0), C.c_int(0), C.c_int(0)
+    pi, pj, pa = C.POINTER(C.c_int)(), C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+    hostlib.chk(hostlib.lib().MatSeqAIJGetCSRB200(A, C.byref(m), C.byref(nn), C.byref(nnz), C.byref(pi), C.byref(pj), C.byref(pa)))
+    ai = np.ctypeslib.as_array(pi, shape=(m.value + 1,)).copy()
+    aj = np.ctypeslib.as_array(pj, shape=(nnz.value,)).copy()
+    aa = np.ctypeslib.as_array(pa, shape=(nnz.value,)).copy()
+    p = oracle.poisson7(*dims)
+    assert m.value == n and np.array_equal(ai, p["ai"]) and np.array_equal(aj, p["aj"])
+    assert np.array_equal(aa, p["aa"])
+    assert np.array_equal(hostlib.vec_array(rhs, n), p["rhs"])
+    assert np.array_equal(hostlib.vec_array(exact, n), p["exact"])
+    assert np.array_equal(hostlib.vec_array(lhs, n), np.zeros(n))
+    hostlib.chk(R.destroySystem(C.byref(da), C.byref(A), C.byref(lhs), C.byref(rhs), C.byref(exact)))

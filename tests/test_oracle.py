@@ -36,6 +36,42 @@ def test_golden_seq(case):
     assert sha(oracle.matmulttranspose(p["ai"], p["aj"], p["aa"], x, N ** 3)) == case["yt_rand"]
 
 
+needs_ref = pytest.mark.skipif(oracle.ref_lib() is None,
+                               reason="oracle/_ref is built only where the reference tree is mounted (make -C oracle)")
+
+
+@needs_ref
+@pytest.mark.parametrize("case", GOLD["seq"], ids=lambda c: f"N{c['N']}")
+def test_reference_loop_text_reproduces_the_golden_checksums(case):
+    """oracle/_ref = the reference's OWN row loops (the PETSc 3.7.6 loop on the old side of
+    src/openacc-step1/MatMult_SeqAIJ.patch:19-32, and the author's host + device loops of
+    src/openacc-step3/MatMult_SeqAIJ.patch:36-70) compiled from where they lie.  They give the bits
+    the golden file holds -- i.e. the goldens are the reference's outputs, not only the port's."""
+    N = case["N"]
+    p = oracle.poisson7(N)
+    x = gen.uniform_pm1(N ** 3, seed=0xB200)
+    assert sha(oracle.ref_matmult(p["ai"], p["aj"], p["aa"], x)) == case["y_rand"]
+    assert sha(oracle.ref_matmult(p["ai"], p["aj"], p["aa"], p["exact"])) == case["y_exact"]
+    for host_rows in (0, 1, N ** 3 // 3, N ** 3):   # where the "transfer" ends the host loop
+        assert sha(oracle.ref_matmult(p["ai"], p["aj"], p["aa"], x, "step3", host_rows)) == case["y_rand"]
+    assert sha(oracle.ref_matmult_mt(p["ai"], p["aj"], p["aa"], x, 7)) == case["y_rand"]
+
+
+@needs_ref
+def test_port_equals_the_reference_loop_on_irregular_matrices():
+    rng = np.random.default_rng(11)
+    cases = [gen.random_csr(700, 500, 40, rng, empty_frac=0.3), gen.powerlaw(5000, lmax=800), gen.stencil27(7, seed=2)]
+    for ai, aj, aa in cases:
+        n = int(aj.max()) + 1 if len(aj) else 1
+        x = gen.uniform_pm1(n, 9)
+        ref = oracle.ref_matmult(ai, aj, aa, x)
+        assert np.array_equal(oracle.matmult(ai, aj, aa, x), ref)
+        assert np.array_equal(oracle.matmult_mt(ai, aj, aa, x, 3), ref)
+        assert np.array_equal(oracle.ref_matmult(ai, aj, aa, x, "step3", len(ai) // 2), ref)
+        # MatMultAdd restates the same loop with the accumulator started at y: adding to zero is the same sum
+        assert np.array_equal(oracle.matmultadd(ai, aj, aa, x, np.zeros(len(ai) - 1)), ref)
+
+
 @pytest.mark.parametrize("case", GOLD["mpi"], ids=lambda c: f"N{c['N']}x{c['size']}")
 def test_golden_mpi(case):
     N, size = case["N"], case["size"]
