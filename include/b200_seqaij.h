@@ -60,7 +60,9 @@ enum {
   B200_KERNEL_VECTOR = 3,  /* sub-warp per row, __shfl_xor reduction                             */
   B200_KERNEL_MERGE  = 4,  /* skewed rows: nnz-balanced whole-row tiles + a warp per long row (exact
                               order); B200_MERGE_SPLIT=1: split-row tiles with carry fix-up       */
-  B200_KERNEL_CPROW  = 5   /* compressed-row: only the non-empty rows                            */
+  B200_KERNEL_CPROW  = 5,  /* compressed-row: only the non-empty rows                            */
+  B200_KERNEL_SELL   = 6   /* the optional SELL-32-sigma copy (b200_csr_build_sell); never chosen by
+                              AUTO                                                               */
 };
 
 typedef struct b200_csr_s *b200_csr_t;
@@ -80,6 +82,9 @@ typedef struct {
   int32_t index8_diagonals;  /* > 0: column indices stream as 1-byte codes over this many diagonals */
   int32_t hist[16];          /* row-length histogram: [0],[1],[2],[3-4],[5-8],...,[>16384]      */
   uint64_t device_bytes;     /* HBM held by this handle                                         */
+  int32_t sell_chunks;       /* > 0: a SELL-32-sigma copy is resident (chunks of 32 rows)          */
+  int32_t sell_sigma;        /* its sorting window                                               */
+  uint64_t sell_padded_nnz;  /* entries it stores, padding included                              */
 } b200_csr_info_t;
 
 /* ---- runtime ------------------------------------------------------------------------------ */
@@ -107,6 +112,20 @@ int b200_csr_get_info(b200_csr_t A, b200_csr_info_t *info);
 int b200_csr_set_kernel(b200_csr_t A, int kernel); /* B200_KERNEL_* override, AUTO resets     */
 /* Build (or drop) the explicit transpose used by the deterministic MatMultTranspose.         */
 int b200_csr_build_transpose(b200_csr_t A);
+/* Optional SELL-32-sigma (sliced ELLPACK) copy for stencil-like matrices: chunks of 32 rows
+ * stored column-major and padded to the chunk's longest row; inside windows of `sigma` rows the
+ * rows are ordered by decreasing length first (sigma = 1: natural order, no permutation array).
+ * With a byte-code plan (<= 254 diagonals) the copy holds 1-byte codes too.  Used by
+ * b200_csr_set_kernel(A, B200_KERNEL_SELL); dropped by b200_csr_update_values.  Padding is
+ * skipped, so every mode sums a row left to right exactly like the CSR kernels.               */
+int b200_csr_build_sell(b200_csr_t A, int32_t sigma);
+/* The packing itself, host only (no device needed): sizes first, then the arrays
+ * cs[nchunks + 1] (chunk starts, in entries), perm[nchunks * 32] (slot -> row, -1 = padding slot),
+ * val[padded], col[padded] (-1 = padding entry).                                              */
+int b200_sell_pack_size(int32_t m, const int32_t *h_ai, int32_t sigma, int32_t *nchunks,
+                        uint64_t *padded);
+int b200_sell_pack(int32_t m, const int32_t *h_ai, const int32_t *h_aj, const double *h_aa,
+                   int32_t sigma, uint32_t *cs, int32_t *perm, double *val, int32_t *col);
 /* Device pointers of the mirrors (for tests / composition), any may be NULL.                 */
 int b200_csr_device_arrays(b200_csr_t A, const int32_t **d_ai, const int32_t **d_aj,
                            const double **d_aa);

@@ -22,8 +22,8 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libb200aij.so")
 
 MODE_FAST, MODE_EXACT, MODE_EXACT_FMA = 0, 1, 2
-KERNEL_AUTO, KERNEL_ROW, KERNEL_STREAM, KERNEL_VECTOR, KERNEL_MERGE, KERNEL_CPROW = range(6)
-KERNEL_NAMES = {0: "auto", 1: "row", 2: "stream", 3: "vector", 4: "merge", 5: "cprow"}
+KERNEL_AUTO, KERNEL_ROW, KERNEL_STREAM, KERNEL_VECTOR, KERNEL_MERGE, KERNEL_CPROW, KERNEL_SELL = range(7)
+KERNEL_NAMES = {0: "auto", 1: "row", 2: "stream", 3: "vector", 4: "merge", 5: "cprow", 6: "sell"}
 
 
 class B200Error(RuntimeError):
@@ -55,7 +55,8 @@ class CsrInfo(C.Structure):
                 ("vector_lanes", C.c_int32), ("stream_tiles", C.c_int32),
                 ("merge_tiles", C.c_int32), ("has_transpose", C.c_int32),
                 ("index8_diagonals", C.c_int32),
-                ("hist", C.c_int32 * 16), ("device_bytes", C.c_uint64)]
+                ("hist", C.c_int32 * 16), ("device_bytes", C.c_uint64),
+                ("sell_chunks", C.c_int32), ("sell_sigma", C.c_int32), ("sell_padded_nnz", C.c_uint64)]
 
 
 class CgResult(C.Structure):
@@ -78,6 +79,7 @@ ABI_SYMBOLS = [
     "b200_host_unregister", "b200_vec_set", "b200_vec_copy", "b200_vec_axpy", "b200_vec_aypx",
     "b200_vec_pointwise_mult", "b200_vec_dot", "b200_vec_norm2", "b200_vec_norm_inf",
     "b200_vec_sum", "b200_cg_jacobi", "b200_gen_vector",
+    "b200_csr_build_sell", "b200_sell_pack_size", "b200_sell_pack",
 ]
 
 
@@ -167,6 +169,10 @@ class Csr:
     def build_transpose(self):
         check(lib.b200_csr_build_transpose(self._h))
 
+    def build_sell(self, sigma=1):
+        """The optional SELL-32-sigma copy; use it with set_kernel(KERNEL_SELL)."""
+        check(lib.b200_csr_build_sell(self._h, C.c_int32(sigma)))
+
     # device-resident vectors (torch CUDA tensors)
     def mult(self, x, y, mode=MODE_FAST, stream=None):
         check(lib.b200_spmv(self._h, _dptr(x), _dptr(y), C.c_int(mode), _stream(stream)))
@@ -224,6 +230,23 @@ class Csr:
         check(lib.b200_cg_jacobi(self._h, _dptr(b), _dptr(x), C.c_double(rtol), C.c_double(atol),
                                  C.c_int32(max_it), C.c_int(mode), C.byref(res), _stream(stream)))
         return res
+
+
+def sell_pack(ai, aj, aa, sigma=1):
+    """Host packing of the SELL-32-sigma copy (no device needed): (cs, perm, val, col)."""
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    aj = np.ascontiguousarray(aj, dtype=np.int32)
+    aa = np.ascontiguousarray(aa, dtype=np.float64)
+    m = len(ai) - 1
+    nchunks, padded = C.c_int32(0), C.c_uint64(0)
+    check(lib.b200_sell_pack_size(C.c_int32(m), _np_ptr(ai), C.c_int32(sigma), C.byref(nchunks), C.byref(padded)))
+    cs = np.zeros(nchunks.value + 1, dtype=np.uint32)
+    perm = np.zeros(max(nchunks.value * 32, 1), dtype=np.int32)
+    val = np.zeros(max(padded.value, 1), dtype=np.float64)
+    col = np.zeros(max(padded.value, 1), dtype=np.int32)
+    check(lib.b200_sell_pack(C.c_int32(m), _np_ptr(ai), _np_ptr(aj), _np_ptr(aa), C.c_int32(sigma), _np_ptr(cs), _np_ptr(perm),
+                             _np_ptr(val), _np_ptr(col)))
+    return cs, perm[:nchunks.value * 32], val[:padded.value], col[:padded.value]
 
 
 def gen_vector(n, seed=0xB200):

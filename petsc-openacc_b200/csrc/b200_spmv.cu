@@ -17,10 +17,12 @@
 //   k_vector  LANES lanes per row + __shfl_xor reduction -- override / comparison
 //   k_cprow   compressed-row (only non-empty rows)       -- matrices with >= 60 % empty rows
 //   k_tr_atomic  A^T x by fp64 atomics                   -- transpose without a second copy
-// Why no SELL-C-sigma / sliced-ELL copy: staging the CSR tile in shared memory already gives what
-// those formats buy on a GPU -- the matrix is read in fully coalesced 16-byte-aligned bulk copies and
-// lane = consecutive row makes the x gathers of a stencil contiguous -- without padding, without a
-// second copy of the values, and while keeping the row's CSR order, i.e. the reference's bits.
+//   k_sell    SELL-32-sigma copy (optional, b200_csr_build_sell), column-major chunks of 32 rows,
+//             padding skipped -- override only; not yet measured against k_stream
+// Why the SELL-C-sigma / sliced-ELL copy is not the default: staging the CSR tile in shared memory
+// already gives what those formats buy on a GPU -- the matrix is read in fully coalesced
+// 16-byte-aligned bulk copies and lane = consecutive row makes the x gathers of a stencil
+// contiguous -- without padding and without a second copy of the values.
 #include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
@@ -555,6 +557,61 @@ __global__ void __launch_bounds__(256) k_tr_atomic(int m, const int *__restrict_
   for (int k = lo + lane; k < hi; k += LANES) atomicAdd(y + aj[k], alpha * aa[k]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_sell: SELL-32-sigma (sliced ELLPACK, slice height = one warp).  Rows are grouped in chunks of
+// 32 (inside windows of sigma rows they are first ordered by decreasing length); a chunk stores
+// max-row-length x 32 entries column-major, so lane l's k-th entry sits at base + 32 k + l: every
+// load of values and indices is one contiguous 256- / 128- / 32-byte request without any staging.
+// Padding is marked (column -1, or byte code 255) and SKIPPED, never multiplied, so a row is still
+// summed left to right over exactly its own entries: the bits of the CPU loop.  No row pointers
+// are read (4 bytes per chunk instead of per row).
+// The optional copy the north star lists for stencil matrices; built by b200_csr_build_sell and
+// used only under the B200_KERNEL_SELL override (the stream kernel stays the measured default).
+// ---------------------------------------------------------------------------------------------
+#define SELL_C 32
+#define SELL_U 8
+#define SELL_PAD_CODE 255
+template <int MODE, bool ADD, bool IDX8, bool PERM>
+__global__ void __launch_bounds__(256)
+    k_sell(int m, int nchunks, const unsigned int *__restrict__ cs, const double *__restrict__ val,
+           const int *__restrict__ col, const unsigned char *__restrict__ code, const int *__restrict__ offs,
+           const int *__restrict__ perm, const double *__restrict__ x, const double *yin, double *y)
+{
+  __shared__ int soffs[256];
+  if (IDX8) {
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) soffs[t] = __ldg(offs + t);
+    __syncthreads();
+  }
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = (int)(slot >> 5), lane = (int)(slot & 31);
+  if (chunk >= nchunks) return;
+  const int row = PERM ? __ldg(perm + slot) : (slot < m ? (int)slot : -1);   // -1: padding slot
+  const unsigned int base = __ldg(cs + chunk);
+  const int len = (int)((__ldg(cs + chunk + 1) - base) >> 5);
+  double sum = (ADD && row >= 0) ? yin[row] : 0.0;
+  const uint64_t pol = l2_policy_evict_first();
+  for (int k = 0; k < len; k += SELL_U) {
+    double a[SELL_U], xv[SELL_U];
+    int    c[SELL_U];
+#pragma unroll
+    for (int j = 0; j < SELL_U; ++j) {
+      const bool   ok = (k + j) < len;
+      const size_t at = (size_t)base + (size_t)(k + j) * SELL_C + lane;
+      a[j] = ok ? ldg_f64_stream_policy(val + at, pol) : 0.0;
+      if (IDX8) {
+        const int cd = ok ? (int)__ldg(code + at) : SELL_PAD_CODE;
+        c[j] = (cd == SELL_PAD_CODE) ? -1 : row + soffs[cd];
+      } else c[j] = ok ? ldg_s32_stream_policy(col + at, pol) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < SELL_U; ++j) xv[j] = (c[j] >= 0) ? __ldg(x + c[j]) : 0.0;
+#pragma unroll
+    for (int j = 0; j < SELL_U; ++j)
+      if (c[j] >= 0) sum = acc<MODE>(sum, a[j], xv[j]);
+  }
+  if (row >= 0) y[row] = sum;
+}
+
 // ---- device-side transpose build (setup, once per matrix) ------------------------------------
 // row id of every non-zero (thread per row), column histogram, and the gather through the sorted
 // permutation; the stable radix sort by column keeps ascending row order inside each column.
@@ -618,6 +675,13 @@ struct b200_csr_s {
   int4   *d_xtiles = nullptr;
   int    *d_longrows = nullptr;
   int32_t nxtiles = 0, nlong = 0;
+  // optional SELL-32-sigma copy (b200_csr_build_sell)
+  double        *d_sval = nullptr;
+  int           *d_scol = nullptr, *d_sperm = nullptr;
+  unsigned char *d_scode = nullptr;
+  unsigned int  *d_scs = nullptr;
+  int32_t        sell_chunks = 0, sell_sigma = 0;
+  uint64_t       sell_padded = 0;
   // vector plan
   int32_t vector_lanes = 8;
   int32_t kernel_fast = B200_KERNEL_ROW, kernel_exact = B200_KERNEL_ROW, kernel_override = 0;
@@ -1106,11 +1170,22 @@ extern "C" int b200_csr_create_from_device(b200_csr_t *out, int32_t m, int32_t n
   return B200_OK;
 }
 
+static void sell_drop(b200_csr_s *A)
+{
+  cudaFree(A->d_sval); cudaFree(A->d_scol); cudaFree(A->d_sperm); cudaFree(A->d_scode); cudaFree(A->d_scs);
+  A->d_sval = nullptr; A->d_scol = nullptr; A->d_sperm = nullptr; A->d_scode = nullptr; A->d_scs = nullptr;
+  A->sell_chunks = 0; A->sell_sigma = 0; A->sell_padded = 0;
+}
+
 extern "C" int b200_csr_update_values(b200_csr_t A, const double *h_aa)
 {
   if (!A || (!h_aa && A->nz)) return set_error(B200_ERR_ARG, "b200_csr_update_values: bad argument");
   if (A->nz) B200_CUDA_TRY(cudaMemcpy(A->d_aa, h_aa, (size_t)A->nz * sizeof(double), cudaMemcpyHostToDevice));
   if (A->T) { b200_csr_destroy(A->T); A->T = nullptr; }  // stale transpose values
+  if (A->sell_chunks) {                                  // stale SELL values: back to the plan's kernel
+    sell_drop(A);
+    if (A->kernel_override == B200_KERNEL_SELL) A->kernel_override = 0;
+  }
   return B200_OK;
 }
 
@@ -1123,6 +1198,7 @@ extern "C" int b200_csr_destroy(b200_csr_t A)
   cudaFree(A->d_aj8); cudaFree(A->d_offs);
   cudaFree(A->d_mtiles); cudaFree(A->d_msplit); cudaFree(A->d_mhead); cudaFree(A->d_mtail);
   cudaFree(A->d_xtiles); cudaFree(A->d_longrows);
+  sell_drop(A);
   cudaFree(A->d_hx); cudaFree(A->d_hy);
   for (auto &s : A->hs) if (s) cudaStreamDestroy(s);
   for (auto &e : A->hev) if (e) cudaEventDestroy(e);
@@ -1145,12 +1221,14 @@ extern "C" int b200_csr_get_info(b200_csr_t A, b200_csr_info_t *info)
   info->index8_diagonals = A->idx8 ? A->noffs : 0;
   memcpy(info->hist, A->hist, sizeof A->hist);
   info->device_bytes = A->device_bytes + (A->T ? A->T->device_bytes : 0);
+  info->sell_chunks = A->sell_chunks; info->sell_sigma = A->sell_sigma; info->sell_padded_nnz = A->sell_padded;
   return B200_OK;
 }
 
 extern "C" int b200_csr_set_kernel(b200_csr_t A, int kernel)
 {
-  if (!A || kernel < 0 || kernel > B200_KERNEL_CPROW) return set_error(B200_ERR_ARG, "b200_csr_set_kernel: bad argument");
+  if (!A || kernel < 0 || kernel > B200_KERNEL_SELL) return set_error(B200_ERR_ARG, "b200_csr_set_kernel: bad argument");
+  if (kernel == B200_KERNEL_SELL && !A->sell_chunks) return set_error(B200_ERR_STATE, "no SELL copy: call b200_csr_build_sell first");
   if (kernel == B200_KERNEL_STREAM && !A->ntiles) return set_error(B200_ERR_STATE, "stream kernel not applicable: a row exceeds the stage capacity");
   if (kernel == B200_KERNEL_CPROW && !A->cprow_use) return set_error(B200_ERR_STATE, "matrix has no compressed-row index");
   if (kernel == B200_KERNEL_MERGE && !A->nmtiles) {
@@ -1270,12 +1348,156 @@ static int launch_mode(b200_csr_s *A, int kernel, const double *x, const double 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// SELL-32-sigma copy: host packing (pure host code, also exported for the CPU tests), upload, launch
+// ---------------------------------------------------------------------------------------------
+// Slot order: inside every window of `sigma` rows, rows by decreasing length (stable, so sigma = 1
+// or equal lengths keep the natural order); slots past the last row are padding (-1).
+static void sell_order(int32_t m, const int32_t *ai, int32_t sigma, std::vector<int32_t> &order)
+{
+  const size_t nslots = ((size_t)m + SELL_C - 1) / SELL_C * SELL_C;
+  order.assign(nslots, -1);
+  for (int32_t r = 0; r < m; ++r) order[r] = r;
+  if (sigma > 1)
+    for (int64_t w = 0; w < m; w += sigma)
+      std::stable_sort(order.begin() + w, order.begin() + std::min<int64_t>(m, w + sigma),
+                       [&](int32_t a, int32_t b) { return ai[a + 1] - ai[a] > ai[b + 1] - ai[b]; });
+}
+
+extern "C" int b200_sell_pack_size(int32_t m, const int32_t *h_ai, int32_t sigma, int32_t *nchunks, uint64_t *padded)
+{
+  if (m < 0 || (m && !h_ai) || sigma < 1 || !nchunks || !padded) return set_error(B200_ERR_ARG, "b200_sell_pack_size: bad argument");
+  std::vector<int32_t> order;
+  sell_order(m, h_ai, sigma, order);
+  const int32_t nc = (int32_t)(order.size() / SELL_C);
+  uint64_t tot = 0;
+  for (int32_t c = 0; c < nc; ++c) {
+    int32_t len = 0;
+    for (int l = 0; l < SELL_C; ++l) { const int32_t r = order[(size_t)c * SELL_C + l]; if (r >= 0) len = std::max(len, h_ai[r + 1] - h_ai[r]); }
+    tot += (uint64_t)len * SELL_C;
+  }
+  *nchunks = nc; *padded = tot;
+  return B200_OK;
+}
+
+// cs[nchunks + 1], perm[nchunks * 32], val[padded], col[padded] (col -1 = padding)
+extern "C" int b200_sell_pack(int32_t m, const int32_t *h_ai, const int32_t *h_aj, const double *h_aa, int32_t sigma,
+                              uint32_t *cs, int32_t *perm, double *val, int32_t *col)
+{
+  if (m < 0 || sigma < 1 || !cs || (m && (!h_ai || !perm))) return set_error(B200_ERR_ARG, "b200_sell_pack: bad argument");
+  std::vector<int32_t> order;
+  sell_order(m, h_ai, sigma, order);
+  const int32_t nc = (int32_t)(order.size() / SELL_C);
+  uint64_t tot = 0;
+  cs[0] = 0;
+  for (int32_t c = 0; c < nc; ++c) {
+    int32_t len = 0;
+    for (int l = 0; l < SELL_C; ++l) { const int32_t r = order[(size_t)c * SELL_C + l]; if (r >= 0) len = std::max(len, h_ai[r + 1] - h_ai[r]); }
+    tot += (uint64_t)len * SELL_C;
+    if (tot > 0xFFFFFFFFull) return set_error(B200_ERR_ARG, "SELL copy exceeds 2^32 entries");
+    cs[c + 1] = (uint32_t)tot;
+  }
+  std::copy(order.begin(), order.end(), perm);
+  const int nt = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  auto fill = [&](int t) {
+    for (int32_t c = (int32_t)((int64_t)nc * t / nt); c < (int32_t)((int64_t)nc * (t + 1) / nt); ++c) {
+      const int32_t len = (int32_t)((cs[c + 1] - cs[c]) / SELL_C);
+      for (int l = 0; l < SELL_C; ++l) {
+        const int32_t r = order[(size_t)c * SELL_C + l];
+        const int32_t n = (r >= 0) ? h_ai[r + 1] - h_ai[r] : 0;
+        for (int32_t k = 0; k < len; ++k) {
+          const size_t at = (size_t)cs[c] + (size_t)k * SELL_C + l;
+          val[at] = (k < n) ? h_aa[h_ai[r] + k] : 0.0;
+          col[at] = (k < n) ? h_aj[h_ai[r] + k] : -1;
+        }
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(fill, t);
+  fill(0);
+  for (auto &x : th) x.join();
+  return B200_OK;
+}
+
+extern "C" int b200_csr_build_sell(b200_csr_t A, int32_t sigma)
+{
+  NvtxRange nvtx_("b200_csr_build_sell");
+  if (!A || sigma < 1) return set_error(B200_ERR_ARG, "b200_csr_build_sell: bad argument");
+  B200_TRY(ensure_device());
+  sell_drop(A);
+  if (A->kernel_override == B200_KERNEL_SELL) A->kernel_override = 0;
+  if (A->m == 0) return B200_OK;
+  std::vector<int32_t> ai((size_t)A->m + 1), aj((size_t)std::max(A->nz, 1));
+  std::vector<double>  aa((size_t)std::max(A->nz, 1));
+  B200_CUDA_TRY(cudaMemcpy(ai.data(), A->d_ai, ai.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  if (A->nz) {
+    B200_CUDA_TRY(cudaMemcpy(aj.data(), A->d_aj, (size_t)A->nz * sizeof(int), cudaMemcpyDeviceToHost));
+    B200_CUDA_TRY(cudaMemcpy(aa.data(), A->d_aa, (size_t)A->nz * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  int32_t  nc = 0;
+  uint64_t padded = 0;
+  B200_TRY(b200_sell_pack_size(A->m, ai.data(), sigma, &nc, &padded));
+  std::vector<uint32_t> cs((size_t)nc + 1);
+  std::vector<int32_t>  perm((size_t)nc * SELL_C), col((size_t)std::max<uint64_t>(padded, 1));
+  std::vector<double>   val((size_t)std::max<uint64_t>(padded, 1));
+  B200_TRY(b200_sell_pack(A->m, ai.data(), aj.data(), aa.data(), sigma, cs.data(), perm.data(), val.data(), col.data()));
+  B200_TRY(dev_alloc(&A->d_scs, cs.size(), A));
+  B200_TRY(dev_alloc(&A->d_sval, val.size(), A));
+  B200_CUDA_TRY(cudaMemcpy(A->d_scs, cs.data(), cs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  B200_CUDA_TRY(cudaMemcpy(A->d_sval, val.data(), val.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (sigma > 1) {
+    B200_TRY(dev_alloc(&A->d_sperm, perm.size(), A));
+    B200_CUDA_TRY(cudaMemcpy(A->d_sperm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  if (A->idx8 && A->noffs < SELL_PAD_CODE) {
+    // one byte per entry: the code of its diagonal (col - row), 255 = padding
+    std::vector<int> offs(256);
+    B200_CUDA_TRY(cudaMemcpy(offs.data(), A->d_offs, 256 * sizeof(int), cudaMemcpyDeviceToHost));
+    offs.resize((size_t)A->noffs);
+    std::vector<unsigned char> code(col.size(), SELL_PAD_CODE);
+    for (int32_t c = 0; c < nc; ++c)
+      for (size_t at = cs[c]; at < cs[c + 1]; ++at) {
+        if (col[at] < 0) continue;
+        const int32_t r = perm[(size_t)c * SELL_C + (at - cs[c]) % SELL_C];
+        code[at] = (unsigned char)(std::lower_bound(offs.begin(), offs.end(), col[at] - r) - offs.begin());
+      }
+    B200_TRY(dev_alloc(&A->d_scode, code.size(), A));
+    B200_CUDA_TRY(cudaMemcpy(A->d_scode, code.data(), code.size(), cudaMemcpyHostToDevice));
+  } else {
+    B200_TRY(dev_alloc(&A->d_scol, col.size(), A));
+    B200_CUDA_TRY(cudaMemcpy(A->d_scol, col.data(), col.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  A->sell_chunks = nc; A->sell_sigma = sigma; A->sell_padded = padded;
+  return B200_OK;
+}
+
+template <bool ADD>
+static int launch_sell(b200_csr_s *A, const double *x, const double *yin, double *y, int mode, cudaStream_t st)
+{
+  if (!A->sell_chunks) return set_error(B200_ERR_STATE, "no SELL copy: call b200_csr_build_sell first");
+  const unsigned grid = (unsigned)(((size_t)A->sell_chunks * SELL_C + 255) / 256);
+#define B200_SELL_GO(MODE_, I8, PM)                                                                                   \
+  B200_LAUNCH((k_sell<MODE_, ADD, I8, PM>), grid, 256, 0, st, A->m, A->sell_chunks, A->d_scs, A->d_sval, A->d_scol, \
+              A->d_scode, A->d_offs, A->d_sperm, x, yin, y)
+#define B200_SELL_MODE(MODE_)                                                      \
+  do {                                                                             \
+    if (A->d_scode) { if (A->d_sperm) B200_SELL_GO(MODE_, true, true); else B200_SELL_GO(MODE_, true, false); }   \
+    else { if (A->d_sperm) B200_SELL_GO(MODE_, false, true); else B200_SELL_GO(MODE_, false, false); }            \
+  } while (0)
+  if (mode == B200_MODE_EXACT) B200_SELL_MODE(B200_MODE_EXACT); else B200_SELL_MODE(B200_MODE_EXACT_FMA);
+#undef B200_SELL_MODE
+#undef B200_SELL_GO
+  return B200_OK;
+}
+
 template <bool ADD>
 static int spmv_dispatch(b200_csr_s *A, const double *x, const double *yin, double *y, int mode, cudaStream_t st)
 {
   if (A->m == 0) return B200_OK;
   int kernel = A->kernel_override;
   if (!kernel) kernel = (mode == B200_MODE_FAST) ? A->kernel_fast : A->kernel_exact;
+  if (kernel == B200_KERNEL_SELL) return launch_sell<ADD>(A, x, yin, y, mode, st);
   // Skewed matrices: the exact-order kernels (whole-row tiles + a warp per long row) are also the
   // fastest measured (configs[4]: 1.08 ms vs 1.23 ms for the split-row merge), so FAST uses them too;
   // B200_MERGE_SPLIT=1 keeps the split-row merge kernel reachable for comparison.

@@ -230,6 +230,10 @@ extern "C" PetscErrorCode KSPSetUp(KSP k)
   if (k->mg) { ierr = b200_pcgamg_destroy(&k->mg);CHKERRQ(ierr); }
   if (k->pc == "jacobi") {
     // PCSetUp_Jacobi [P376]: diagonal, reciprocal, zero entries -> 1
+    PetscInt rows, have = -1;
+    ierr = MatGetLocalSize(k->P ? k->P : k->A, &rows, NULL);CHKERRQ(ierr);
+    if (k->dinv) { ierr = VecGetLocalSize(k->dinv, &have);CHKERRQ(ierr); }
+    if (k->dinv && have != rows) { ierr = VecDestroy(&k->dinv);CHKERRQ(ierr); }   // operators of another size were set
     if (!k->dinv) { ierr = MatCreateVecs(k->P ? k->P : k->A, NULL, &k->dinv);CHKERRQ(ierr); }
     ierr = MatGetDiagonal(k->P ? k->P : k->A, k->dinv);CHKERRQ(ierr);
     PetscScalar *d;
