@@ -6,11 +6,15 @@
  * cpu_baseline / --impl reference legs may load this library, and only as the checker or as the
  * timed CPU baseline.  The product (petsc-openacc_b200/) never links or calls it.
  *
- * PARITY UNPINNED (bit level): the reference (olcf/PETSC-OpenACC) ships no golden vectors, no
- * tests and no logs, and the arithmetic lives in PETSc 3.7.6 (petsc-lite-3.7.6.tar.gz, sha1
- * f2310cc0663848cbdcdf2ddf8ac48246a43d336b, scripts/petsc.sh:39,45) which is downloaded at build
- * time and is neither under /root/reference nor installable here (no network, no MPI).  What pins
- * this file instead:
+ * PINNED: orc_matmult equals, bit for bit, the reference's own row loops compiled from its patch
+ * files (oracle/_ref/libref_matmult.so: extract_ref_loops.py + ref_harness.c; tests/test_oracle.py),
+ * and the generator below equals the reference's own src/helper.cpp compiled from where it lies
+ * (oracle/_ref/libref_helper.so; tests/test_host_layer.py).
+ * PARITY UNPINNED for everything else: the reference (olcf/PETSC-OpenACC) ships no golden
+ * vectors, no tests and no logs, and the rest of the arithmetic lives in PETSc 3.7.6
+ * (petsc-lite-3.7.6.tar.gz, sha1 f2310cc0663848cbdcdf2ddf8ac48246a43d336b, scripts/petsc.sh:39,45)
+ * which is downloaded at build time and is neither under /root/reference nor installable here (no
+ * network, no MPI).  What this file follows:
  *   - the MatMult loop is visible verbatim as context lines of the reference's own patches
  *     (src/openacc-step1/MatMult_SeqAIJ.patch:22-32) and is restated by the reference author in
  *     plain C at src/openacc-step3/MatMult_SeqAIJ.patch:38-48; orc_matmult follows those lines;
