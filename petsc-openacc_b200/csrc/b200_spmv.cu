@@ -571,6 +571,32 @@ __global__ void __launch_bounds__(256) k_tr_atomic(int m, const int *__restrict_
 #define SELL_C 32
 #define SELL_U 8
 #define SELL_PAD_CODE 255
+// `asm volatile` loads: the compiler keeps them in program order (8 values, 8 indices, then 8
+// gathers issued back to back) instead of sinking each load next to its use
+__device__ __forceinline__ double sell_ld_f64_stream(const double *p, uint64_t pol)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int sell_ld_s32_stream(const int *p, uint64_t pol)
+{
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int sell_ld_u8_stream(const unsigned char *p, uint64_t pol)
+{
+  unsigned int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return (int)v;
+}
+__device__ __forceinline__ double sell_ld_f64(const double *p)
+{
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 template <int MODE, bool ADD, bool IDX8, bool PERM>
 __global__ void __launch_bounds__(256)
     k_sell(int m, int nchunks, const unsigned int *__restrict__ cs, const double *__restrict__ val,
@@ -591,20 +617,24 @@ __global__ void __launch_bounds__(256)
   double sum = (ADD && row >= 0) ? yin[row] : 0.0;
   const uint64_t pol = l2_policy_evict_first();
   for (int k = 0; k < len; k += SELL_U) {
+    // three passes so that the 8 value loads, the 8 index loads and then the 8 gathers are all in
+    // flight together: every load is unconditional (the arrays carry SELL_U * 32 entries of tail
+    // padding, a gather of an absent entry reads x[0]) and only the adds are predicated
     double a[SELL_U], xv[SELL_U];
     int    c[SELL_U];
 #pragma unroll
     for (int j = 0; j < SELL_U; ++j) {
-      const bool   ok = (k + j) < len;
       const size_t at = (size_t)base + (size_t)(k + j) * SELL_C + lane;
-      a[j] = ok ? ldg_f64_stream_policy(val + at, pol) : 0.0;
-      if (IDX8) {
-        const int cd = ok ? (int)__ldg(code + at) : SELL_PAD_CODE;
-        c[j] = (cd == SELL_PAD_CODE) ? -1 : row + soffs[cd];
-      } else c[j] = ok ? ldg_s32_stream_policy(col + at, pol) : -1;
+      a[j] = sell_ld_f64_stream(val + at, pol);
+      c[j] = IDX8 ? sell_ld_u8_stream(code + at, pol) : sell_ld_s32_stream(col + at, pol);
     }
 #pragma unroll
-    for (int j = 0; j < SELL_U; ++j) xv[j] = (c[j] >= 0) ? __ldg(x + c[j]) : 0.0;
+    for (int j = 0; j < SELL_U; ++j) {
+      const bool ok = (k + j) < len;
+      if (IDX8) c[j] = (ok && c[j] != SELL_PAD_CODE) ? row + soffs[c[j]] : -1;
+      else if (!ok) c[j] = -1;
+      xv[j] = sell_ld_f64(x + (c[j] >= 0 ? c[j] : 0));
+    }
 #pragma unroll
     for (int j = 0; j < SELL_U; ++j)
       if (c[j] >= 0) sum = acc<MODE>(sum, a[j], xv[j]);
@@ -1442,6 +1472,10 @@ extern "C" int b200_csr_build_sell(b200_csr_t A, int32_t sigma)
   std::vector<int32_t>  perm((size_t)nc * SELL_C), col((size_t)std::max<uint64_t>(padded, 1));
   std::vector<double>   val((size_t)std::max<uint64_t>(padded, 1));
   B200_TRY(b200_sell_pack(A->m, ai.data(), aj.data(), aa.data(), sigma, cs.data(), perm.data(), val.data(), col.data()));
+  // the kernel reads up to SELL_U - 1 chunk columns past a chunk's end without a bounds test
+  const size_t tail = (size_t)SELL_U * SELL_C;
+  val.resize(val.size() + tail, 0.0);
+  col.resize(col.size() + tail, -1);
   B200_TRY(dev_alloc(&A->d_scs, cs.size(), A));
   B200_TRY(dev_alloc(&A->d_sval, val.size(), A));
   B200_CUDA_TRY(cudaMemcpy(A->d_scs, cs.data(), cs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
