@@ -212,3 +212,52 @@ def cg_mg(levels, b, rtol=1e-14, atol=1e-12, max_it=10000, sweeps=1):
     lib().orc_cg_mg.restype = C.c_int
     its = lib().orc_cg_mg(*pk.args(sweeps), _p(b), _p(x), C.c_double(rtol), C.c_double(atol), C.c_int(max_it), C.byref(rn))
     return x, its, rn.value
+
+
+# ---- row-partitioned variant (petsc-openacc_b200/dgamg.py) -------------------------------------------
+def uncoupled_hierarchy(A, base, threshold=0.0, nsmooths=1, coarse_eq_limit=50, max_levels=30, square_graph=1):
+    """Restatement of dgamg.setup on the GLOBAL matrix `A` (scipy CSR, rows in rank order, partition
+    `base`): aggregates inside each rank's diagonal block, prolongator smoothed with that block
+    (P = blockdiag(P_r)), emax = global Gershgorin bound, Galerkin product on the global matrices.
+    Returns (levels, bases): levels as in `hierarchy`, bases[l] = row partition of level l."""
+    A = A.tocsr()
+    A.sort_indices()
+    levels = [dict(A=A, P=None, agg=None, nagg=0, emax=0.0)]
+    B = np.ones(A.shape[0])
+    bases = [np.asarray(base, dtype=np.int64)]
+    while len(levels) < max_levels:
+        l = len(levels) - 1
+        A, base = levels[l]["A"], bases[l]
+        m = A.shape[0]
+        if l > 0 and m <= coarse_eq_limit:
+            break
+        d = A.diagonal()
+        emax = gershgorin_emax(A, d)
+        blocks, Bcs, aggs, naggs = [], [], [], []
+        for r in range(len(base) - 1):
+            lo, hi = int(base[r]), int(base[r + 1])
+            Ad = A[lo:hi, lo:hi].tocsr()
+            Ad.sort_indices()
+            adj, dd = strength_graph(Ad.indptr, Ad.indices, Ad.data, threshold)
+            agg, nagg = aggregate(adj, l < square_graph)
+            P0, Bc = tentative(agg, nagg, B[lo:hi])
+            if nsmooths == 1 and nagg:
+                dinv = np.where(dd != 0.0, 1.0 / np.where(dd != 0.0, dd, 1.0), 1.0)
+                P = (P0 - (1.4 / emax) * (sp.diags(dinv) @ (Ad @ P0))).tocsr()
+            else:
+                P = P0.tocsr()
+            blocks.append(P)
+            Bcs.append(Bc)
+            aggs.append(agg)
+            naggs.append(nagg)
+        if min(naggs) == 0 or sum(naggs) >= m:
+            break
+        P = sp.block_diag(blocks, format="csr")
+        P.sort_indices()
+        Ac = (P.T @ (A @ P)).tocsr()
+        Ac.sort_indices()
+        levels[l].update(P=P, agg=aggs, nagg=sum(naggs), emax=emax)
+        levels.append(dict(A=Ac, P=None, agg=None, nagg=0, emax=0.0))
+        B = np.concatenate(Bcs)
+        bases.append(np.concatenate([[0], np.cumsum(naggs)]).astype(np.int64))
+    return levels, bases

@@ -617,3 +617,134 @@ PetscErrorCode b200_pcgamg_destroy(B200PCGamg **pmg)
   *pmg = NULL;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Host CSR utilities and one coarsening step behind a C ABI (include/b200_gamg.h): the pieces the
+// row-partitioned multigrid set-up (petsc-openacc_b200/dgamg.py, one process per GPU) composes.
+// Same kernels as the single-process set-up above; no device code.
+// ---------------------------------------------------------------------------------------------
+#include "../../../include/b200_gamg.h"
+
+struct b200_hcsr_s { Csr c; };
+
+namespace {
+int hcsr_fail(int code, const char *what)
+{
+  PetscError(PETSC_COMM_SELF, __LINE__, "b200_hcsr", __FILE__, code, "%s", what);
+  return code;
+}
+}  // namespace
+
+extern "C" int b200_hcsr_create(b200_hcsr_t *out, int32_t m, int32_t n, const int32_t *ai, const int32_t *aj, const double *aa)
+{
+  if (!out || m < 0 || n < 0 || !ai || ai[0] != 0) return hcsr_fail(PETSC_ERR_ARG_OUTOFRANGE, "bad CSR");
+  for (int32_t r = 0; r < m; ++r) {
+    if (ai[r + 1] < ai[r]) return hcsr_fail(PETSC_ERR_ARG_OUTOFRANGE, "row pointers decrease");
+    for (int32_t k = ai[r]; k < ai[r + 1]; ++k)
+      if (aj[k] < 0 || aj[k] >= n || (k > ai[r] && aj[k] <= aj[k - 1])) return hcsr_fail(PETSC_ERR_ARG_WRONG, "columns out of range or not strictly ascending");
+  }
+  b200_hcsr_s *h = new b200_hcsr_s;
+  h->c.m = m; h->c.n = n;
+  h->c.i.assign(ai, ai + m + 1);
+  h->c.j.assign(aj, aj + ai[m]);
+  h->c.a.assign(aa, aa + ai[m]);
+  *out = h;
+  return 0;
+}
+extern "C" int b200_hcsr_destroy(b200_hcsr_t h) { delete h; return 0; }
+extern "C" int b200_hcsr_shape(b200_hcsr_t h, int32_t *m, int32_t *n, int32_t *nz)
+{
+  if (!h) return hcsr_fail(PETSC_ERR_ARG_WRONG, "null handle");
+  if (m) *m = h->c.m;
+  if (n) *n = h->c.n;
+  if (nz) *nz = h->c.i.empty() ? 0 : h->c.i[h->c.m];
+  return 0;
+}
+extern "C" int b200_hcsr_arrays(b200_hcsr_t h, const int32_t **ai, const int32_t **aj, const double **aa)
+{
+  if (!h) return hcsr_fail(PETSC_ERR_ARG_WRONG, "null handle");
+  if (ai) *ai = h->c.i.data();
+  if (aj) *aj = h->c.j.data();
+  if (aa) *aa = h->c.a.data();
+  return 0;
+}
+extern "C" int b200_hcsr_spgemm(b200_hcsr_t X, b200_hcsr_t Y, b200_hcsr_t *out)
+{
+  if (!X || !Y || !out) return hcsr_fail(PETSC_ERR_ARG_WRONG, "null handle");
+  b200_hcsr_s *h = new b200_hcsr_s;
+  int rc = spgemm(X->c.view(), Y->c.view(), h->c);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return 0;
+}
+extern "C" int b200_hcsr_transpose(b200_hcsr_t X, b200_hcsr_t *out)
+{
+  if (!X || !out) return hcsr_fail(PETSC_ERR_ARG_WRONG, "null handle");
+  b200_hcsr_s *h = new b200_hcsr_s;
+  transpose(X->c.view(), h->c);
+  *out = h;
+  return 0;
+}
+// X + Y (same shape): an entry present in both is x + y, otherwise the one that is there
+extern "C" int b200_hcsr_add(b200_hcsr_t X, b200_hcsr_t Y, b200_hcsr_t *out)
+{
+  if (!X || !Y || !out) return hcsr_fail(PETSC_ERR_ARG_WRONG, "null handle");
+  if (X->c.m != Y->c.m || X->c.n != Y->c.n) return hcsr_fail(PETSC_ERR_ARG_SIZ, "b200_hcsr_add: shapes differ");
+  b200_hcsr_s *h = new b200_hcsr_s;
+  const Csr &x = X->c, &y = Y->c;
+  int rc = build_rows(x.m, x.n, true, h->c, [&](int, PetscInt r, std::vector<PetscInt> &cj, std::vector<MatScalar> &ca) {
+    PetscInt k = x.i[r], l = y.i[r];
+    const PetscInt ke = x.i[r + 1], le = y.i[r + 1];
+    while (k < ke || l < le) {
+      if (l >= le || (k < ke && x.j[k] < y.j[l])) { cj.push_back(x.j[k]); ca.push_back(x.a[k]); ++k; }
+      else if (k >= ke || y.j[l] < x.j[k]) { cj.push_back(y.j[l]); ca.push_back(y.a[l]); ++l; }
+      else { cj.push_back(x.j[k]); ca.push_back(x.a[k] + y.a[l]); ++k; ++l; }
+    }
+  });
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return 0;
+}
+extern "C" int b200_hcsr_abs_row_sums(b200_hcsr_t A, double *out)
+{
+  if (!A || (!out && A->c.m)) return hcsr_fail(PETSC_ERR_ARG_WRONG, "null argument");
+  for (PetscInt r = 0; r < A->c.m; ++r) {
+    double s = 0.0;
+    for (PetscInt k = A->c.i[r]; k < A->c.i[r + 1]; ++k) s += std::fabs(A->c.a[k]);
+    out[r] = s;
+  }
+  return 0;
+}
+
+// One coarsening step on a square block (a whole matrix, or one rank's diagonal block): strength
+// graph, greedy MIS aggregates (of the squared graph when `square`), tentative prolongator from B,
+// and, when emax > 0, one smoothing step P = (I - 1.4/emax D^-1 A) P0 with this block as A.
+extern "C" int b200_gamg_coarsen_block(b200_hcsr_t A, const double *B, double threshold, int square, double emax,
+                                       int32_t *agg_out, int32_t *nagg_out, b200_hcsr_t *P_out, double *Bc_out)
+{
+  if (!A || !agg_out || !nagg_out || !P_out || (A->c.m && (!B || !Bc_out))) return hcsr_fail(PETSC_ERR_ARG_WRONG, "null argument");
+  if (A->c.m != A->c.n) return hcsr_fail(PETSC_ERR_ARG_SIZ, "b200_gamg_coarsen_block: square block expected");
+  const CsrView          Av = A->c.view();
+  std::vector<MatScalar> d;
+  diagonal(Av, d);
+  Csr G;
+  int rc = strength_graph(Av, d, threshold, G);
+  if (rc) return rc;
+  std::vector<PetscInt> agg;
+  const PetscInt        nagg = aggregate(G, square != 0, agg);
+  std::copy(agg.begin(), agg.end(), agg_out);
+  *nagg_out = nagg;
+  std::vector<MatScalar> Bv(B, B + A->c.m), Bc;
+  b200_hcsr_s *h = new b200_hcsr_s;
+  Csr          P0;
+  tentative_prolongator(agg, nagg, Bv, P0, Bc);
+  if (emax > 0.0 && nagg > 0) {
+    Csr AP0;
+    rc = spgemm(Av, P0.view(), AP0);
+    if (!rc) rc = smooth_prolongator(AP0, P0, d, -1.4 / emax, h->c);
+    if (rc) { delete h; return rc; }
+  } else h->c = std::move(P0);
+  std::copy(Bc.begin(), Bc.end(), Bc_out);
+  *P_out = h;
+  return 0;
+}

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(pk):
     libs = {"b200_seqaij.h": pk.lib, "b200_mpiaij.h": pk.lib}
     host = os.path.join(ROOT, "petsc-openacc_b200", "libb200petsc.so")
     if os.path.exists(host):
-        libs["b200_petsc_symbols.h"] = C.CDLL(host)
+        libs["b200_petsc_symbols.h"] = libs["b200_gamg.h"] = C.CDLL(host)
     decl = declared_symbols()
     assert len([1 for f, _ in decl if f == "b200_seqaij.h"]) >= 30
     for fn, name in sorted(decl):

@@ -1,0 +1,164 @@
+"""Row-partitioned multigrid set-up (petsc-openacc_b200/dgamg.py, BASELINE configs[2]): every rank
+builds its rows of every level; the assembled hierarchy must equal the global restatement
+oracle/gamg.py::uncoupled_hierarchy.  All ranks run as threads of this process (ThreadComm) and, once,
+as two gloo processes (TorchComm).  The device solve of dgamg.Solver has not run on a GPU yet: its
+test is behind B200_EXPERIMENTAL=1."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from oracle import gamg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def global_problem(N, size):
+    base = oracle.dmda_bases(N, N, N, size)
+    parts = [oracle.poisson7(N, size=size, rank=r) for r in range(size)]
+    A = sp.vstack([sp.csr_matrix((p["aa"], p["aj"], p["ai"]), shape=(len(p["ai"]) - 1, N ** 3)) for p in parts]).tocsr()
+    return A, base, parts
+
+
+def assemble(levels_per_rank, l):
+    """Global CSR of level l from the ranks' row blocks, and the block-diagonal prolongator."""
+    rows = [lv[l].rows for lv in levels_per_rank]
+    n = int(levels_per_rank[0][l].base[-1])
+    A = sp.vstack([sp.csr_matrix((aa, aj, ai), shape=(len(ai) - 1, n)) for ai, aj, aa in rows]).tocsr()
+    P = None
+    if levels_per_rank[0][l].P is not None:
+        P = sp.block_diag([sp.csr_matrix((lv[l].P[2], lv[l].P[1], lv[l].P[0]), shape=(len(lv[l].P[0]) - 1, lv[l].P[3]))
+                           for lv in levels_per_rank], format="csr")
+    return A, P
+
+
+@pytest.mark.parametrize("N,size", [(10, 2), (12, 4), (12, 8), (9, 3)])
+def test_distributed_setup_equals_the_global_restatement(pk, N, size):
+    from petsc_openacc_b200 import dgamg
+    A, base, parts = global_problem(N, size)
+
+    def rank_main(comm):
+        p = parts[comm.rank]
+        return dgamg.setup(comm, base, p["ai"], p["aj"], p["aa"])
+
+    per_rank = dgamg.ThreadComm.run(size, rank_main)
+    want, bases = gamg.uncoupled_hierarchy(A, base)
+    nlev = len(per_rank[0])
+    assert all(len(lv) == nlev for lv in per_rank) and nlev == len(want) >= 3
+    for l in range(nlev):
+        assert np.array_equal(per_rank[0][l].base, bases[l])
+        Al, Pl = assemble(per_rank, l)
+        Al.eliminate_zeros()
+        W = want[l]["A"].copy()
+        W.eliminate_zeros()
+        assert Al.shape == W.shape
+        assert abs(Al - W).max() <= 1e-12 * abs(W).max()
+        assert np.array_equal(Al.indptr, W.indptr) and np.array_equal(Al.indices, W.indices)
+        if want[l]["P"] is not None:
+            for r in range(size):
+                assert np.array_equal(per_rank[r][l].agg, want[l]["agg"][r])      # integer work: bit-exact
+                assert per_rank[r][l].emax == pytest.approx(want[l]["emax"], rel=1e-14)
+            Pl.eliminate_zeros()
+            assert abs(Pl - want[l]["P"]).max() <= 1e-12 * abs(want[l]["P"]).max()
+        else:
+            assert Pl is None
+        dinv = np.concatenate([lv[l].dinv for lv in per_rank])
+        assert np.array_equal(dinv, 1.0 / Al.diagonal())
+    # what it is for: CG + V-cycle on this hierarchy (C restatement) converges like the one-rank hierarchy
+    rhs = np.concatenate([p["rhs"] for p in parts])
+    x, its, rn = gamg.cg_mg(want, rhs)
+    p1 = oracle.poisson7(N)
+    _, its1, _ = gamg.cg_mg(gamg.hierarchy(p1["ai"], p1["aj"], p1["aa"]), p1["rhs"])
+    assert 0 < its <= its1 + 14
+    for lv in per_rank:
+        for L in lv:
+            L.M.destroy()
+
+
+WORKER = r'''
+import os, sys, pickle
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np
+import torch.distributed as dist
+import oracle
+from petsc_openacc_b200 import dgamg
+dist.init_process_group("gloo")
+comm = dgamg.TorchComm()
+N = 10
+base = oracle.dmda_bases(N, N, N, comm.size)
+p = oracle.poisson7(N, size=comm.size, rank=comm.rank)
+lv = dgamg.setup(comm, base, p["ai"], p["aj"], p["aa"])
+out = [dict(base=L.base, rows=L.rows, P=L.P, agg=L.agg, emax=L.emax) for L in lv]
+with open(os.path.join(sys.argv[1], f"rank{comm.rank}.pkl"), "wb") as f:
+    pickle.dump(out, f)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_distributed_setup_over_two_gloo_processes(pk, tmp_path):
+    import pickle
+    from petsc_openacc_b200 import dgamg
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29671", str(script), str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    got = [pickle.load(open(tmp_path / f"rank{r}.pkl", "rb")) for r in range(2)]
+    N = 10
+    A, base, parts = global_problem(N, 2)
+
+    def rank_main(comm):
+        p = parts[comm.rank]
+        return dgamg.setup(comm, base, p["ai"], p["aj"], p["aa"])
+
+    same = dgamg.ThreadComm.run(2, rank_main)                     # the threads and the processes agree bit for bit
+    for r in range(2):
+        assert len(got[r]) == len(same[r])
+        for g, L in zip(got[r], same[r]):
+            assert np.array_equal(g["base"], L.base)
+            for k in range(3):
+                assert np.array_equal(g["rows"][k], L.rows[k])
+            if L.P is not None:
+                for k in range(3):
+                    assert np.array_equal(g["P"][k], L.P[k])
+                assert np.array_equal(g["agg"], L.agg) and g["emax"] == L.emax
+    for lv in same:
+        for L in lv:
+            L.M.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL", "0") != "1",
+                    reason="dgamg.Solver has not run on a GPU yet (round-1 budget spent): B200_EXPERIMENTAL=1 enables it")
+@pytest.mark.parametrize("N,size", [(12, 2), (16, 4)])
+def test_device_solve_in_process_ranks(pk, cuda, N, size):
+    """All ranks on one device (threads, split-phase halo): the CG + V-cycle solve against the C
+    restatement on the assembled global hierarchy."""
+    torch = cuda
+    from petsc_openacc_b200 import dgamg
+    A, base, parts = global_problem(N, size)
+    want, _ = gamg.uncoupled_hierarchy(A, base)
+    rhs = np.concatenate([p["rhs"] for p in parts])
+    xo, its_o, _ = gamg.cg_mg(want, rhs)
+
+    def rank_main(comm):
+        p = parts[comm.rank]
+        lv = dgamg.setup(comm, base, p["ai"], p["aj"], p["aa"])
+        sv = dgamg.Solver(comm, lv)
+        b = torch.from_numpy(p["rhs"]).cuda()
+        x = torch.zeros_like(b)
+        its, reason, rn = sv.solve(b, x)
+        out = (its, reason, x.cpu().numpy())
+        sv.destroy()
+        return out
+
+    res = dgamg.ThreadComm.run(size, rank_main)
+    assert all(r[1] > 0 for r in res) and len({r[0] for r in res}) == 1
+    assert abs(res[0][0] - its_o) <= 1
+    x = np.concatenate([r[2] for r in res])
+    assert np.abs(x - xo).max() <= 1e-9 * np.abs(xo).max()
