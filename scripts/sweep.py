@@ -73,6 +73,16 @@ def main():
     report("vector (auto lanes=%d)" % info.vector_lanes, A, pk.MODE_FAST, pk.KERNEL_VECTOR)
     report("stream default exact", A, pk.MODE_EXACT, pk.KERNEL_STREAM)
     report("stream default fma", A, pk.MODE_EXACT_FMA, pk.KERNEL_STREAM)
+    # the optional SELL-32-sigma copy (k_sell): sigma = 1 keeps the natural row order
+    for sigma in (1, 4096):
+        try:
+            A.build_sell(sigma)
+        except pk.B200Error as e:
+            print(f"sell sigma={sigma}: n/a ({e})")
+            continue
+        pad = A.info().sell_padded_nnz / max(nz, 1)
+        report(f"sell-32-{sigma} exact (padding x{pad:.3f})", A, pk.MODE_EXACT, pk.KERNEL_SELL)
+        report(f"sell-32-{sigma} fma", A, pk.MODE_EXACT_FMA, pk.KERNEL_SELL)
     A.destroy()
     mean = nz / m
     for threads in (256, 128):
