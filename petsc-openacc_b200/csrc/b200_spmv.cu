@@ -1048,7 +1048,11 @@ static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
   A->kernel_exact = A->cprow_use ? B200_KERNEL_CPROW : (A->ntiles ? B200_KERNEL_STREAM : B200_KERNEL_ROW);
   // FAST: rows of similar, short length -> stream (SIMT lanes stay balanced);
   //       otherwise sub-warp vector kernel.
-  const bool regular = A->rmax <= std::max(32.0, 4.0 * mean);
+  // B200_MERGE_MEAN_ABOVE=k (experiment, off by default): uniformly LONG rows (mean > k; the coarse
+  // multigrid operators have 100-200 entries per row) also take the exact-order merge kernels --
+  // a stream tile holds only cap/mean rows, so most of its consumer threads would idle.
+  const int  merge_mean_above = env_int("B200_MERGE_MEAN_ABOVE", 0);
+  const bool regular = A->rmax <= std::max(32.0, 4.0 * mean) && (merge_mean_above <= 0 || mean <= merge_mean_above);
   if (A->cprow_use) A->kernel_fast = B200_KERNEL_CPROW;
   else if (A->ntiles && regular) A->kernel_fast = B200_KERNEL_STREAM;
   else if (A->nz > 0) {
