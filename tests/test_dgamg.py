@@ -162,3 +162,51 @@ def test_device_solve_in_process_ranks(pk, cuda, N, size):
     assert abs(res[0][0] - its_o) <= 1
     x = np.concatenate([r[2] for r in res])
     assert np.abs(x - xo).max() <= 1e-9 * np.abs(xo).max()
+
+
+# ---- the host CSR kernels behind include/b200_gamg.h ---------------------------------------------------
+def _rand(m, n, density, rng):
+    M = sp.random(m, n, density=density, random_state=np.random.RandomState(int(rng.integers(1 << 30))), format="csr")
+    M.sort_indices()
+    return M
+
+
+def test_host_csr_kernels_against_scipy(pk):
+    from petsc_openacc_b200 import dgamg
+    rng = np.random.default_rng(12)
+    for (m, k, n) in [(1, 1, 1), (40, 30, 50), (300, 300, 300), (25000, 900, 700)]:   # the last one runs threaded
+        X, Y, Z = _rand(m, k, min(1.0, 6.0 / k), rng), _rand(k, n, min(1.0, 5.0 / n), rng), _rand(m, k, min(1.0, 4.0 / k), rng)
+        hX = dgamg.HostCsr.from_arrays(m, k, X.indptr, X.indices, X.data)
+        hY = dgamg.HostCsr.from_arrays(k, n, Y.indptr, Y.indices, Y.data)
+        hZ = dgamg.HostCsr.from_arrays(m, k, Z.indptr, Z.indices, Z.data)
+
+        def back(h, shape):
+            ai, aj, aa = h.arrays()
+            assert all(np.all(np.diff(aj[ai[r]:ai[r + 1]]) > 0) for r in range(min(shape[0], 500)))   # ascending, unique
+            return sp.csr_matrix((aa, aj, ai), shape=shape)
+
+        P = back(hX.matmul(hY), (m, n))
+        W = (X @ Y).tocsr()
+        assert abs(P - W).max() <= 1e-13 * max(abs(W).max(), 1e-300) if W.nnz else P.nnz == 0 or abs(P).max() == 0
+        T = back(hX.transpose(), (k, m))
+        assert (T != X.T.tocsr()).nnz == 0
+        S = back(hX.add(hZ), (m, k))
+        assert abs(S - (X + Z)).max() <= 1e-15 * max(abs(X + Z).max(), 1e-300) if (X + Z).nnz else True
+        assert np.allclose(hX.abs_row_sums(), np.asarray(abs(X).sum(axis=1)).ravel(), rtol=1e-14, atol=0)
+        for h in (hX, hY, hZ):
+            h.destroy()
+
+
+def test_host_csr_rejects_bad_input(pk):
+    from petsc_openacc_b200 import dgamg
+    with pytest.raises(RuntimeError):
+        dgamg.HostCsr.from_arrays(2, 3, [0, 2, 3], [1, 0, 2], [1.0, 2.0, 3.0])      # columns not ascending
+    with pytest.raises(RuntimeError):
+        dgamg.HostCsr.from_arrays(1, 2, [0, 1], [5], [1.0])                          # column out of range
+    a = dgamg.HostCsr.from_arrays(2, 3, [0, 1, 2], [0, 2], [1.0, 2.0])
+    b = dgamg.HostCsr.from_arrays(2, 2, [0, 1, 2], [0, 1], [1.0, 2.0])
+    with pytest.raises(RuntimeError):
+        a.matmul(b)                                                                  # 3 columns x 2 rows
+    with pytest.raises(RuntimeError):
+        a.add(b)
+    a.destroy(); b.destroy()
