@@ -96,8 +96,8 @@ void parallel_blocks(PetscInt m, F f)
 // Rows of a CSR built independently: `row(t, r, j, a)` appends the entries of row r (ascending
 // columns) to the calling thread's buffers.  Row blocks run on the set-up threads; the blocks are
 // then laid end to end, so the result does not depend on the thread count.
-template <class RowFn>
-PetscErrorCode build_rows(PetscInt m, PetscInt n, bool values, Csr &C, RowFn row)
+template <class RowFn, class BoundFn>
+PetscErrorCode build_rows(PetscInt m, PetscInt n, bool values, Csr &C, RowFn row, BoundFn bound)
 {
   const int nt = (m < 20000) ? 1 : setup_threads();
   struct Part { std::vector<PetscInt> len, j; std::vector<MatScalar> a; };
@@ -105,6 +105,10 @@ PetscErrorCode build_rows(PetscInt m, PetscInt n, bool values, Csr &C, RowFn row
   parallel_blocks(m, [&](int t, PetscInt r0, PetscInt r1) {
     Part &p = parts[t];
     p.len.resize((size_t)(r1 - r0));
+    // room for the most this block can produce: untouched pages cost nothing, regrowing does
+    const size_t most = bound(r0, r1);
+    p.j.reserve(most);
+    if (values) p.a.reserve(most);
     for (PetscInt r = r0; r < r1; ++r) {
       const size_t before = p.j.size();
       row(t, r, p.j, p.a);
@@ -129,6 +133,11 @@ PetscErrorCode build_rows(PetscInt m, PetscInt n, bool values, Csr &C, RowFn row
   C.i[m] = (PetscInt)first[nt];
   return 0;
 }
+template <class RowFn>
+PetscErrorCode build_rows(PetscInt m, PetscInt n, bool values, Csr &C, RowFn row)
+{
+  return build_rows(m, n, values, C, row, [](PetscInt, PetscInt) { return (size_t)0; });
+}
 
 // C = X * Y, row by row with a dense accumulator; every entry is summed over X's row in storage
 // order (then over Y's row).
@@ -152,6 +161,10 @@ PetscErrorCode spgemm(const CsrView &X, const CsrView &Y, Csr &C)
     }
     std::sort(w.cols.begin(), w.cols.end());
     for (PetscInt c : w.cols) { cj.push_back(c); ca.push_back(w.acc[c]); }
+  }, [&](PetscInt r0, PetscInt r1) {
+    size_t most = 0;   // every term of the block's rows lands in a column of its own
+    for (PetscInt k = X.i[r0]; k < X.i[r1]; ++k) most += (size_t)(Y.i[X.j[k] + 1] - Y.i[X.j[k]]);
+    return std::min(most, (size_t)(r1 - r0) * (size_t)std::max(Y.n, 1));
   });
 }
 
