@@ -79,8 +79,9 @@ def ref_matmult(ai, aj, aa, x, variant="original", host_rows=0):
     y = np.empty(m, dtype=np.float64)
     if variant == "original":
         L.ref_matmult_original(C.c_int(m), _p(ai), _p(aj), _p(aa), _p(x), _p(y))
-    elif variant == "step3":
-        L.ref_matmult_step3(C.c_int(m), _p(ai), _p(aj), _p(aa), _p(x), _p(y), C.c_int(host_rows))
+    elif variant in ("step3", "step4"):   # step4: the device loop in blocks of 983,040 rows
+        f = L.ref_matmult_step3 if variant == "step3" else L.ref_matmult_step4
+        f(C.c_int(m), _p(ai), _p(aj), _p(aa), _p(x), _p(y), C.c_int(host_rows))
     else:
         raise ValueError(variant)
     return y

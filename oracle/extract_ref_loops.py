@@ -8,6 +8,9 @@ as include fragments into oracle/_ref/ (git-ignored; nothing of the reference en
   matmult_step3_host.inc      new side ('+' and context lines) of src/openacc-step3/
                               MatMult_SeqAIJ.patch from `PetscInt offset = 0;` to the end of the
                               device loop: the reference author's host loop + kernel loop
+  matmult_step4_blocked.inc   the same region of src/openacc-step4/MatMult_SeqAIJ.patch: host loop,
+                              the row-blocked kernel loops (983,040 rows per block) and the loop
+                              over the remaining rows
 
 usage: python extract_ref_loops.py <reference root> <output dir>
 """
@@ -52,7 +55,10 @@ def main(ref, out):
     loop = block_from(old1, r"for \(i=0; i<m; i\+\+\) \{", r"for \(i=0; i<m; i\+\+\) \{")
     _, new3 = sides(os.path.join(ref, "src/openacc-step3/MatMult_SeqAIJ.patch"))
     host = block_from(new3, r"PetscInt offset = 0;", r"for \(i=offset; i<m; i\+\+\) \{")
-    for name, lines in (("matmult_original_loop.inc", loop), ("matmult_step3_host.inc", host)):
+    _, new4 = sides(os.path.join(ref, "src/openacc-step4/MatMult_SeqAIJ.patch"))
+    blocked = block_from(new4, r"PetscInt offset = 0;", r"for \(i=offset; i<m; i\+\+\) \{")
+    for name, lines in (("matmult_original_loop.inc", loop), ("matmult_step3_host.inc", host),
+                        ("matmult_step4_blocked.inc", blocked)):
         with open(os.path.join(out, name), "w") as f:
             f.write("\n".join(lines) + "\n")
         print(f"{name}: {len(lines)} lines")

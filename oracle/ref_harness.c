@@ -7,8 +7,9 @@
  *
  * What is the reference's: the loop bodies -- src/openacc-step1/MatMult_SeqAIJ.patch:19-32, old
  * side = PETSc 3.7.6's loop as the patch shows it; src/openacc-step3/MatMult_SeqAIJ.patch:36-70,
- * new side = the author's host loop followed by the device loop, whose `# pragma acc` lines a
- * plain C compiler ignores.
+ * new side = the author's host loop followed by the device loop; src/openacc-step4/
+ * MatMult_SeqAIJ.patch:36-88 = the same with the device loop cut into row blocks.  A plain C
+ * compiler ignores their `# pragma acc` lines.
  * What is NOT in the reference and is supplied here: the declarations around the fragments (they
  * are PETSc's, visible only as names in the patches) and the PetscSparseDensePlusDot macro, which
  * lives in PETSc 3.7.6's private headers [P376]; its default variant is restated below, as in
@@ -54,6 +55,18 @@ void ref_matmult_step3(PetscInt m, const PetscInt *ii, const PetscInt *cols, con
   const MatScalar *aa;
   PetscScalar      sum;
 #include "matmult_step3_host.inc"
+}
+
+/* Step 4: as step 3, but the device part is cut into blocks of 983,040 rows (one kernel launch and
+ * one y download per block, src/openacc-step4/MatMult_SeqAIJ.patch:51-72) plus the remaining rows. */
+void ref_matmult_step4(PetscInt m, const PetscInt *ii, const PetscInt *cols, const MatScalar *data,
+                       const PetscScalar *x, PetscScalar *y, PetscInt host_rows)
+{
+  PetscInt         i, n;
+  const PetscInt  *aj;
+  const MatScalar *aa;
+  PetscScalar      sum;
+#include "matmult_step4_blocked.inc"
 }
 #undef acc_async_test_all
 

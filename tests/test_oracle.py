@@ -54,7 +54,19 @@ def test_reference_loop_text_reproduces_the_golden_checksums(case):
     assert sha(oracle.ref_matmult(p["ai"], p["aj"], p["aa"], p["exact"])) == case["y_exact"]
     for host_rows in (0, 1, N ** 3 // 3, N ** 3):   # where the "transfer" ends the host loop
         assert sha(oracle.ref_matmult(p["ai"], p["aj"], p["aa"], x, "step3", host_rows)) == case["y_rand"]
+        assert sha(oracle.ref_matmult(p["ai"], p["aj"], p["aa"], x, "step4", host_rows)) == case["y_rand"]
     assert sha(oracle.ref_matmult_mt(p["ai"], p["aj"], p["aa"], x, 7)) == case["y_rand"]
+
+
+@needs_ref
+def test_reference_blocked_loop_with_a_full_block():
+    """Step 4 cuts the rows into blocks of 983,040: a matrix long enough for one whole block plus a
+    remainder, host loop stopped early -- same bits as the plain loop."""
+    ai, aj, aa = gen.poisson7_natural(110, refpoint=False)      # 1,331,000 rows
+    x = gen.uniform_pm1(110 ** 3, 5)
+    ref = oracle.matmult(ai, aj, aa, x)
+    for host_rows in (0, 1000):
+        assert np.array_equal(oracle.ref_matmult(ai, aj, aa, x, "step4", host_rows), ref)
 
 
 @needs_ref
