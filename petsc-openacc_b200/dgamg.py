@@ -283,16 +283,15 @@ def setup(comm, base, ai, aj_global, aa, threshold=0.0, nsmooths=1, coarse_eq_li
 
 
 # ---- device solve ------------------------------------------------------------------------------------
-class Solver:
-    """Uploads a hierarchy and runs KSPCG preconditioned by its V-cycle.  Collective over `comm`.
-    NOT YET RUN ON A GPU (see the module docstring)."""
+class DeviceOps:
+    """Everything the solve does on the GPU, one method per PETSc call.  Vectors are torch CUDA
+    tensors of this rank's rows.  (tests/test_dgamg.py substitutes a numpy/oracle stand-in with the
+    same methods to check the orchestration of `Solver` on the CPU.)"""
 
-    def __init__(self, comm, levels, sweeps=1, mode=MODE_EXACT):
+    def __init__(self, comm, levels, mode=MODE_EXACT):
         import torch
-        self.torch, self.comm, self.levels, self.sweeps, self.mode = torch, comm, levels, int(sweeps), mode
-        dev = torch.device("cuda", torch.cuda.current_device())
-        self.dev = dev
-        f64 = dict(dtype=torch.float64, device=dev)
+        self.torch, self.comm, self.mode = torch, comm, mode
+        self.dev = torch.device("cuda", torch.cuda.current_device())
         for L in levels:
             L.M.upload()
         if comm.inprocess:
@@ -312,18 +311,25 @@ class Solver:
                 for q in range(comm.size):
                     L.M.set_rank_window(q, handle=hl[q] if q != comm.rank else None)
         for L in levels:
-            n = L.M.nloc
-            L.d_dinv = torch.from_numpy(L.dinv).to(dev)
-            L.d_b, L.d_x, L.d_t, L.d_r = (torch.zeros(max(n, 1), **f64)[:n] for _ in range(4))
             L.Pdev = None
             if L.P is not None:
                 Pi, Pj, Pa, nc = L.P
                 L.Pdev = Csr(Pi, Pj, Pa, n=max(nc, 1))
                 L.Pdev.build_transpose()
-        self.scal = torch.zeros(3, **f64)
+        self.allreduce_level = levels[0]
+        self.scal = torch.zeros(3, dtype=torch.float64, device=self.dev)
+
+    def zeros(self, n):
+        return self.torch.zeros(max(n, 1), dtype=self.torch.float64, device=self.dev)[:n]
+
+    def from_numpy(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
+
+    def to_numpy(self, t):
+        return t.cpu().numpy()
 
     # y = A x on level L (MatMult_MPIAIJ); split-phase when all ranks share one device and one stream
-    def _mult(self, L, x, y):
+    def mult(self, L, x, y):
         if self.comm.inprocess:
             L.M.mult_begin(x)
             self.comm.barrier()
@@ -332,41 +338,35 @@ class Solver:
         else:
             L.M.mult(x, y, self.mode)
 
-    def _residual(self, L, b, x, r):
-        from . import vec_aypx
-        self._mult(L, x, r)
-        vec_aypx(r, -1.0, b)                      # r = b - A x        (VecAYPX(r, -1, b))
-
-    def _sweep(self, L, b, x):
-        from . import vec_axpy, vec_pointwise_mult
-        self._residual(L, b, x, L.d_r)
-        vec_pointwise_mult(L.d_r, L.d_dinv, L.d_r)  # z = dinv .* r
-        vec_axpy(x, 1.0, L.d_r)                     # x = x + z
-
-    def _cycle(self, l, b, x):
-        from . import vec_pointwise_mult
-        L = self.levels[l]
-        if l + 1 == len(self.levels):
-            vec_pointwise_mult(x, b, L.d_dinv)
-            return
-        vec_pointwise_mult(x, b, L.d_dinv)          # first sweep from the zero guess
-        for _ in range(self.sweeps - 1):
-            self._sweep(L, b, x)
-        self._residual(L, b, x, L.d_t)
-        C_ = self.levels[l + 1]
+    def restrict(self, L, r, bc):          # MatRestrict: b_c = P^T r, this rank's block
         if L.M.nloc:
-            L.Pdev.mult_transpose(L.d_t, C_.d_b, self.mode)      # restriction: local block
-        self._cycle(l + 1, C_.d_b, C_.d_x)
-        if L.M.nloc and C_.M.nloc:
-            L.Pdev.mult_add(C_.d_x, x, x, self.mode)             # interpolation: local block
-        for _ in range(self.sweeps):
-            self._sweep(L, b, x)
+            L.Pdev.mult_transpose(r, bc, self.mode)
 
-    def apply(self, r, z):
-        """z = M^-1 r: one V-cycle."""
-        self._cycle(0, r, z)
+    def interp_add(self, L, xc, x):        # MatInterpolateAdd: x = x + P x_c, this rank's block
+        if L.M.nloc and len(xc):
+            L.Pdev.mult_add(xc, x, x, self.mode)
 
-    def _dots(self, pairs):
+    def pointwise_mult(self, w, x, y):
+        from . import vec_pointwise_mult
+        vec_pointwise_mult(w, x, y)
+
+    def aypx(self, y, a, x):
+        from . import vec_aypx
+        vec_aypx(y, a, x)
+
+    def axpy(self, y, a, x):
+        from . import vec_axpy
+        vec_axpy(y, a, x)
+
+    def copy(self, y, x):
+        from . import vec_copy
+        vec_copy(y, x)
+
+    def set(self, x, a):
+        from . import vec_set
+        vec_set(x, a)
+
+    def dots(self, pairs):
         """Global dot products, partial sums added in rank order (same bits on every rank)."""
         from . import vec_dot
         for i, (a, b) in enumerate(pairs):
@@ -378,19 +378,64 @@ class Solver:
             for q in range(self.comm.size):
                 tot = tot + parts[q]
             return [float(v) for v in tot]
-        self.levels[0].M.allreduce_sum(self.scal[:len(pairs)])
+        self.allreduce_level.M.allreduce_sum(self.scal[:len(pairs)])
         return [float(v) for v in self.scal[:len(pairs)].cpu()]
+
+    def destroy(self, levels):
+        for L in levels:
+            if getattr(L, "Pdev", None) is not None:
+                L.Pdev.destroy()
+                L.Pdev = None
+
+
+class Solver:
+    """KSPCG preconditioned by the V-cycle of a row-partitioned hierarchy.  Collective over `comm`.
+    The device back end (`DeviceOps`) has NOT YET RUN ON A GPU (see the module docstring)."""
+
+    def __init__(self, comm, levels, sweeps=1, mode=MODE_EXACT, ops=None):
+        self.comm, self.levels, self.sweeps = comm, levels, int(sweeps)
+        self.ops = ops if ops is not None else DeviceOps(comm, levels, mode)
+        for L in levels:
+            n = L.M.nloc
+            L.d_dinv = self.ops.from_numpy(L.dinv)
+            L.d_b, L.d_x, L.d_t, L.d_r = (self.ops.zeros(n) for _ in range(4))
+
+    def _residual(self, L, b, x, r):
+        self.ops.mult(L, x, r)
+        self.ops.aypx(r, -1.0, b)                       # r = b - A x        (VecAYPX(r, -1, b))
+
+    def _sweep(self, L, b, x):
+        self._residual(L, b, x, L.d_r)
+        self.ops.pointwise_mult(L.d_r, L.d_dinv, L.d_r)  # z = dinv .* r
+        self.ops.axpy(x, 1.0, L.d_r)                     # x = x + z
+
+    def _cycle(self, l, b, x):
+        L = self.levels[l]
+        self.ops.pointwise_mult(x, b, L.d_dinv)          # coarse solve, or the first sweep from the zero guess
+        if l + 1 == len(self.levels):
+            return
+        for _ in range(self.sweeps - 1):
+            self._sweep(L, b, x)
+        self._residual(L, b, x, L.d_t)
+        C_ = self.levels[l + 1]
+        self.ops.restrict(L, L.d_t, C_.d_b)
+        self._cycle(l + 1, C_.d_b, C_.d_x)
+        self.ops.interp_add(L, C_.d_x, x)
+        for _ in range(self.sweeps):
+            self._sweep(L, b, x)
+
+    def apply(self, r, z):
+        """z = M^-1 r: one V-cycle."""
+        self._cycle(0, r, z)
 
     def solve(self, b, x, rtol=1e-14, atol=1e-12, max_it=10000):
         """KSPSolve_CG [P376] with the V-cycle; b, x = this rank's rows.  Returns (its, reason, rnorm)."""
-        from . import vec_axpy, vec_aypx, vec_copy, vec_set
-        torch = self.torch
-        L0 = self.levels[0]
-        r, z, p, w = (torch.zeros_like(b) for _ in range(4))
-        vec_set(x, 0.0)
-        vec_copy(r, b)
+        ops, L0 = self.ops, self.levels[0]
+        r, z, p, w = (ops.zeros(L0.M.nloc) for _ in range(4))
+        ops.set(x, 0.0)
+        ops.copy(r, b)
         self.apply(r, z)
-        zz, beta = self._dots([(z, z), (z, r)])
+        zz, beta = ops.dots([(z, z), (z, r)])
         dp = rnorm0 = zz ** 0.5
         ttol = max(rtol * rnorm0, atol)
         it, betaold, reason = 0, 1.0, 0
@@ -401,17 +446,17 @@ class Solver:
                 reason = 3
                 break
             if it == 0:
-                vec_copy(p, z)
+                ops.copy(p, z)
             else:
-                vec_aypx(p, beta / betaold, z)
+                ops.aypx(p, beta / betaold, z)
             betaold = beta
-            self._mult(L0, p, w)
-            (dpi,) = self._dots([(p, w)])
+            ops.mult(L0, p, w)
+            (dpi,) = ops.dots([(p, w)])
             a = beta / dpi
-            vec_axpy(x, a, p)
-            vec_axpy(r, -a, w)
+            ops.axpy(x, a, p)
+            ops.axpy(r, -a, w)
             self.apply(r, z)
-            zz, beta = self._dots([(z, z), (z, r)])
+            zz, beta = ops.dots([(z, z), (z, r)])
             dp = zz ** 0.5
             it += 1
             if dp < ttol:
@@ -422,7 +467,6 @@ class Solver:
         return it, reason, dp
 
     def destroy(self):
+        self.ops.destroy(self.levels)
         for L in self.levels:
-            if getattr(L, "Pdev", None) is not None:
-                L.Pdev.destroy()
             L.M.destroy()

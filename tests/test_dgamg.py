@@ -132,6 +132,105 @@ def test_distributed_setup_over_two_gloo_processes(pk, tmp_path):
             L.M.destroy()
 
 
+class OracleOps:
+    """numpy/oracle stand-in for dgamg.DeviceOps: the same methods on numpy vectors, MatMult_MPIAIJ as
+    PETSc orders it (diagonal block, then MatMultAdd with the ghost values), so that the orchestration
+    of dgamg.Solver -- buffers, order of operations, the CG recurrence -- is checked on the CPU."""
+
+    def __init__(self, comm, levels):
+        self.comm = comm
+        for L in levels:
+            L.blkA, L.blkB = L.M.block(0), L.M.block(1)
+            L.garr, L.roff = L.M.garray(), L.M.recv_offsets()
+
+    def zeros(self, n):
+        return np.zeros(n)
+
+    def from_numpy(self, a):
+        return np.array(a, dtype=np.float64)
+
+    def to_numpy(self, t):
+        return t.copy()
+
+    def mult(self, L, x, y):
+        allx = self.comm.allgather(x.copy())                    # the halo: ghost values from their owners
+        lvec = np.zeros(max(len(L.garr), 1))
+        for q in range(self.comm.size):
+            g = L.garr[L.roff[q]:L.roff[q + 1]]
+            lvec[L.roff[q]:L.roff[q + 1]] = allx[q][g - L.base[q]]
+        Ai, Aj, Aa = L.blkA
+        Bi, Bj, Ba = L.blkB
+        t = oracle.matmult(Ai, Aj, Aa, x) if len(x) else np.zeros(0)
+        y[:] = oracle.matmultadd(Bi, Bj, Ba, lvec, t) if len(x) else t
+
+    def restrict(self, L, r, bc):
+        Pi, Pj, Pa, nc = L.P
+        bc[:] = oracle.matmulttranspose(Pi, Pj, Pa, r, nc)
+
+    def interp_add(self, L, xc, x):
+        Pi, Pj, Pa, nc = L.P
+        x[:] = oracle.matmultadd(Pi, Pj, Pa, xc, x)
+
+    def pointwise_mult(self, w, x, y):
+        w[:] = x * y
+
+    def aypx(self, y, a, x):
+        y[:] = x + a * y
+
+    def axpy(self, y, a, x):
+        y[:] = y + a * x
+
+    def copy(self, y, x):
+        y[:] = x
+
+    def set(self, x, a):
+        x[:] = a
+
+    def dots(self, pairs):
+        parts = self.comm.allgather(np.array([oracle.vecdot(a, b) for a, b in pairs]))
+        tot = np.zeros(len(pairs))
+        for q in range(self.comm.size):
+            tot = tot + parts[q]
+        return [float(v) for v in tot]
+
+    def destroy(self, levels):
+        pass
+
+
+@pytest.mark.parametrize("N,size,sweeps", [(10, 2, 1), (12, 4, 1), (12, 8, 2), (9, 3, 3)])
+def test_solver_orchestration_with_the_oracle_backend(pk, N, size, sweeps):
+    """dgamg.Solver (V-cycle + CG over the ranks) with the CPU stand-in for the device calls against
+    the C restatement on the assembled global hierarchy: same preconditioner, same iteration count."""
+    from petsc_openacc_b200 import dgamg
+    A, base, parts = global_problem(N, size)
+    want, _ = gamg.uncoupled_hierarchy(A, base)
+    rhs = np.concatenate([p["rhs"] for p in parts])
+    r0 = np.concatenate([np.sin(np.arange(len(p["rhs"])) + 3.0 * k) for k, p in enumerate(parts)])
+    z_want = gamg.mg_apply(want, r0, sweeps=sweeps)
+    xo, its_o, _ = gamg.cg_mg(want, rhs, sweeps=sweeps)
+
+    def rank_main(comm):
+        p = parts[comm.rank]
+        lv = dgamg.setup(comm, base, p["ai"], p["aj"], p["aa"])
+        sv = dgamg.Solver(comm, lv, sweeps=sweeps, ops=OracleOps(comm, lv))
+        lo, hi = int(base[comm.rank]), int(base[comm.rank + 1])
+        z = np.full(hi - lo, np.nan)
+        sv.apply(r0[lo:hi].copy(), z)
+        x = np.full(hi - lo, np.nan)
+        its, reason, rn = sv.solve(p["rhs"].copy(), x)
+        sv.destroy()
+        return z, its, reason, x
+
+    res = dgamg.ThreadComm.run(size, rank_main)
+    z = np.concatenate([r[0] for r in res])
+    # MatMult_MPIAIJ adds the ghost terms after the local ones: not the global CSR order, hence a tolerance
+    assert np.abs(z - z_want).max() <= 1e-12 * np.abs(z_want).max()
+    assert all(r[2] > 0 for r in res) and len({r[1] for r in res}) == 1
+    assert abs(res[0][1] - its_o) <= 1
+    x = np.concatenate([r[3] for r in res])
+    assert np.abs(x - xo).max() <= 1e-9 * np.abs(xo).max()
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL", "0") != "1",
                     reason="dgamg.Solver has not run on a GPU yet (round-1 budget spent): B200_EXPERIMENTAL=1 enables it")
