@@ -286,10 +286,14 @@ extern "C" PetscErrorCode VecCopy(Vec x, Vec y)
 {
   if (x->n != y->n) SETERRQ(PETSC_COMM_SELF, PETSC_ERR_ARG_SIZ, "VecCopy: size mismatch");
   if (x == y) return 0;
-  if (x->dev_valid && have_device()) {
+  // on the device when x is current there, or when y has never been touched on the host (a work
+  // vector of a solve: uploading x once is cheaper than giving y a page-locked host array)
+  if (have_device() && (x->dev_valid || !y->array)) {
+    const PetscScalar *dx;
     PetscScalar *d;
-    PetscErrorCode ierr = VecB200GetDeviceArrayWrite(y, &d);CHKERRQ(ierr);
-    B200_CHK(b200_vec_copy(d, x->d_array, x->n, NULL));
+    PetscErrorCode ierr = VecB200GetDeviceArrayRead(x, &dx);CHKERRQ(ierr);
+    ierr = VecB200GetDeviceArrayWrite(y, &d);CHKERRQ(ierr);
+    B200_CHK(b200_vec_copy(d, dx, x->n, NULL));
     return 0;
   }
   PetscErrorCode ierr = vec_host_alloc(x);CHKERRQ(ierr);
