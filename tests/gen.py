@@ -21,10 +21,6 @@ def uniform_pm1(n, seed=0xB200, offset=0):
     return (z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
 
 
-def stencil_csr(N, offsets_fn, value_fn):
-    raise NotImplementedError
-
-
 def poisson7_natural(N, refpoint=True):
     """7-point Neumann Laplacian of src/helper.cpp on one rank (natural ordering), vectorised."""
     n = N ** 3
