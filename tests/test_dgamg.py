@@ -36,7 +36,7 @@ def assemble(levels_per_rank, l):
     return A, P
 
 
-@pytest.mark.parametrize("N,size", [(10, 2), (12, 4), (12, 8), (9, 3)])
+@pytest.mark.parametrize("N,size", [(10, 1), (10, 2), (12, 4), (12, 8), (9, 3)])
 def test_distributed_setup_equals_the_global_restatement(pk, N, size):
     from petsc_openacc_b200 import dgamg
     A, base, parts = global_problem(N, size)
@@ -49,6 +49,11 @@ def test_distributed_setup_equals_the_global_restatement(pk, N, size):
     want, bases = gamg.uncoupled_hierarchy(A, base)
     nlev = len(per_rank[0])
     assert all(len(lv) == nlev for lv in per_rank) and nlev == len(want) >= 3
+    if size == 1:   # one rank: the row-partitioned rule is the one-process set-up of pcgamg.cpp
+        seq = gamg.hierarchy(parts[0]["ai"], parts[0]["aj"], parts[0]["aa"], esteig="gershgorin")
+        assert len(seq) == len(want)
+        for a, b in zip(seq, want):
+            assert abs(a["A"] - b["A"]).max() <= 1e-12 * abs(a["A"]).max()
     for l in range(nlev):
         assert np.array_equal(per_rank[0][l].base, bases[l])
         Al, Pl = assemble(per_rank, l)
