@@ -181,6 +181,7 @@ struct _p_KSP {
   std::string pc = "jacobi";  // PETSc's default for one rank is ilu; the reference always sets -pc_type
   bool fused = false, setup = false;
   bool norm_none = false;     // KSP_NORM_NONE: no convergence test, exactly max_it iterations
+  bool monitor = false, print_reason = false;  // -ksp_monitor, -ksp_converged_reason
   Vec dinv = NULL;
   B200PCGamg *mg = NULL;
   std::vector<PetscReal> *lanczos_d = NULL, *lanczos_e = NULL;  // KSPSetComputeSingularValues
@@ -219,6 +220,10 @@ extern "C" PetscErrorCode KSPSetFromOptions(KSP k)
   }
   ierr = PetscOptionsGetString(NULL, NULL, "-ksp_b200_fused", NULL, 0, &set);CHKERRQ(ierr);
   k->fused = set;
+  ierr = PetscOptionsGetString(NULL, NULL, "-ksp_monitor", NULL, 0, &set);CHKERRQ(ierr);
+  k->monitor = set;
+  ierr = PetscOptionsGetString(NULL, NULL, "-ksp_converged_reason", NULL, 0, &set);CHKERRQ(ierr);
+  k->print_reason = set;
   k->setup = false;
   return 0;
 }
@@ -274,7 +279,7 @@ extern "C" PetscErrorCode KSPSolve(KSP k, Vec b, Vec x)
   ierr = KSPSetUp(k);CHKERRQ(ierr);
   k->reason = KSP_CONVERGED_ITERATING;
   k->its = 0;
-  if (k->fused && k->pc == "jacobi" && !k->norm_none) {
+  if (k->fused && k->pc == "jacobi" && !k->norm_none && !k->monitor) {
     // one-library-call variant: everything (scalars included) stays on the device
     Mat_SeqAIJ *a = (Mat_SeqAIJ *)k->A->data;
     int rc = b200_petsc_ensure_resident(&k->A->spptr, k->A->rmap->n, k->A->cmap->n, a->i, a->j, a->a, (int64_t)k->A->state);
@@ -304,6 +309,8 @@ extern "C" PetscErrorCode KSPSolve(KSP k, Vec b, Vec x)
   rnorm0 = dp;
   k->rnorm = dp;
   PetscInt it = 0;
+  // KSPMonitorDefault's line format [P376]
+  if (k->monitor) { ierr = PetscPrintf(PETSC_COMM_WORLD, "%3d KSP Residual norm %14.12e \n", 0, dp);CHKERRQ(ierr); }
   if (!converged(k, dp, rnorm0, 0)) {
     ierr = VecDot(z, r, &beta);CHKERRQ(ierr);
     PetscScalar dpiold = 0.0;
@@ -334,12 +341,17 @@ extern "C" PetscErrorCode KSPSolve(KSP k, Vec b, Vec x)
       if (!k->norm_none) { ierr = VecNorm(z, NORM_2, &dp);CHKERRQ(ierr); }
       ++it;
       k->rnorm = dp;
+      if (k->monitor) { ierr = PetscPrintf(PETSC_COMM_WORLD, "%3d KSP Residual norm %14.12e \n", it, dp);CHKERRQ(ierr); }
       if (converged(k, dp, rnorm0, it)) break;
       ierr = VecDot(z, r, &beta);CHKERRQ(ierr);
     }
     if (k->reason == KSP_CONVERGED_ITERATING) k->reason = k->norm_none ? KSP_CONVERGED_ITS : KSP_DIVERGED_ITS;
   }
   k->its = it;
+  if (k->print_reason) {
+    ierr = PetscPrintf(PETSC_COMM_WORLD, "Linear solve %s due to reason %d iterations %d\n", k->reason > 0 ? "converged" : "did not converge",
+                       (int)k->reason, it);CHKERRQ(ierr);
+  }
   ierr = VecDestroy(&r);CHKERRQ(ierr);
   ierr = VecDestroy(&z);CHKERRQ(ierr);
   ierr = VecDestroy(&p);CHKERRQ(ierr);
