@@ -142,19 +142,31 @@ def cpu_kernel(oracle):
     return oracle.matmult_mt, "port", "oracle/seqaij_oracle.c orc_matmult_mt"
 
 
+def workload_config(n, gpus, rows, nnz):
+    """`config` of the JSON line: the same dictionary on both arms (the driver compares them)."""
+    if gpus == 1:
+        what = f"3D Poisson 7-point {n}^3 fp64 MatMult_SeqAIJ (BASELINE configs[1])"
+    else:
+        what = f"3D Poisson 7-point {n}^3 fp64 MatMult_MPIAIJ row-partitioned over {gpus} ranks (BASELINE configs[2])"
+    return {"workload": what, "rows": int(rows), "nnz": int(nnz),
+            "algorithmic_bytes": int(algorithmic_bytes(nnz, rows)),
+            "l2": "inputs (2.2-2.8 GB; 280-350 MB per rank at 8) larger than the 126 MB L2; no flush"}
+
+
 def run_reference(args):
     """The reference's CPU MatMult_SeqAIJ loop (its own text from oracle/_ref, or the oracle's
     restatement where that is not built; PETSc as a whole cannot be built offline), one contiguous
-    row block per host thread ~ one MPI rank per core."""
+    row block per host thread ~ one MPI rank per core.  Nothing of the product is imported on this
+    arm: the matrix and x come from the oracle's generator."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import oracle
-    import petsc_openacc_b200 as pk  # generator only (host code); no GPU work on this arm
     n = args.grid
-    ai, aj, aa, _ = gen_poisson(pk, n)
+    p = oracle.poisson7(n)
+    ai, aj, aa = p["ai"], p["aj"], p["aa"]
     m, nnz = len(ai) - 1, len(aj)
-    x = pk.gen_vector(m, 0xB200)
+    x = oracle.gen_vector(m, 0xB200)
     y = np.empty(m)
     cores = host_threads()
     matmult_mt, kind, what = cpu_kernel(oracle)
@@ -170,9 +182,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "gflops": 2.0 * nnz / dt / 1e9,
-        "config": {"workload": f"3D Poisson 7-point {n}^3 fp64 MatMult_SeqAIJ, CPU host threads",
-                   "rows": m, "nnz": nnz, "algorithmic_bytes": algorithmic_bytes(nnz, m)},
+        "config": workload_config(n, args.gpus, m, nnz),
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind,
+                         "flags": "gcc -O2 -ffp-contract=off, no -march (built in the CPU container, runs on the GPU box's host)",
                          "sample": f"{args.steps} full {n}^3 MatMults ({what}), one nnz-balanced row block per thread"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -200,6 +212,7 @@ def cpu_baseline(ai, aj, aa, x, n):
     dt1 = (time.perf_counter() - t1) / 2
     return {"value": algorithmic_bytes(nnz, m) / dt / 1e9, "unit": "GB/s", "cores": cores,
             "kind": kind, "ms_per_matmult": dt * 1e3,
+            "flags": "gcc -O2 -ffp-contract=off, no -march (built in the CPU container, runs on the GPU box's host)",
             "value_1core": algorithmic_bytes(nnz, m) / dt1 / 1e9, "ms_per_matmult_1core": dt1 * 1e3,
             "sample": f"{reps} full {n}^3 MatMults ({what}), one row block per thread"}, y
 
@@ -221,7 +234,7 @@ def run_ours(args):
     pk.init(local)
     if world > 1:
         import bench_mpiaij
-        return bench_mpiaij.run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler)
+        return bench_mpiaij.run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler, workload_config)
 
     n = args.grid
     ai, aj, aa, _ = gen_poisson(pk, n)
@@ -325,11 +338,9 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "gflops": 2.0 * nnz / ms / 1e6,
-        "config": {"workload": f"3D Poisson 7-point {n}^3 fp64 MatMult_SeqAIJ on 1xB200 (BASELINE configs[1])",
-                   "rows": m, "nnz": nnz, "algorithmic_bytes": nbytes, "mode": args.mode,
-                   "kernel": f"k_{kname}", "index8_diagonals": int(info.index8_diagonals),
-                   "l2": "inputs (2.2-2.8 GB) larger than the 126 MB L2; no flush",
-                   "parity_vs_oracle": parity},
+        "config": workload_config(n, 1, m, nnz),
+        "plan": {"mode": args.mode, "kernel": f"k_{kname}", "index8_diagonals": int(info.index8_diagonals),
+                 "parity_vs_oracle": parity},
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": nbytes / e2e_ms / 1e6, "unit": "GB/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": m * 8, "d2h_bytes_per_step": m * 8, "steps": e2e_steps,

@@ -13,7 +13,7 @@ import time
 import numpy as np
 
 
-def run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler):
+def run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler, workload_config):
     import torch
     import torch.distributed as dist
     world = int(os.environ["WORLD_SIZE"])
@@ -170,12 +170,9 @@ def run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler):
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "gflops": 2.0 * nnz_global / ms / 1e6,
-            "config": {"workload": f"3D Poisson 7-point {n}^3 fp64 MatMult_MPIAIJ row-partitioned over {world}xB200 (BASELINE configs[2])",
-                       "rows": rows_global, "nnz": nnz_global, "algorithmic_bytes": nbytes,
-                       "mode": args.mode, "halo": halo, "process_grid": [int(v) for v in g["info"][:3]],
-                       "rows_per_rank": nloc, "nghost_rank0": M.nghost,
-                       "l2": "per-rank inputs larger than L2 up to 8 ranks (349 MB); no flush",
-                       "parity_vs_oracle": parity},
+            "config": workload_config(n, world, rows_global, nnz_global),
+            "plan": {"mode": args.mode, "halo": halo, "process_grid": [int(v) for v in g["info"][:3]],
+                     "rows_per_rank": nloc, "nghost_rank0": M.nghost, "parity_vs_oracle": parity},
             "roofline": {"bound": "hbm", "achieved": value / world, "peak": peak, "unit": "GB/s",
                          "frac": value / world / peak, "traffic": None, "kernel": "k_stream (diagonal block) + k_halo_push + k_offdiag",
                          "peak_source": peak_src, "note": "per-GPU share of the whole-job rate, halo and launches included"},

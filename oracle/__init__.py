@@ -53,6 +53,17 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def gen_vector(n, seed=0xB200):
+    """x[i] = uniform [-1,1) from splitmix64(seed ^ i): the synthetic x of SURVEY 8(d), in numpy, so
+    that the reference arm of bench.py needs nothing of the product package."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) ^ np.arange(n, dtype=np.uint64)) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
+
+
 # ---- oracle/_ref: the reference's own MatMult loops, compiled from its patch files -------------
 _REF_SO = os.path.join(_HERE, "_ref", "libref_matmult.so")
 _ref = None

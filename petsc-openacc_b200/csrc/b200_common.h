@@ -191,7 +191,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-  uint32_t addr = smem_u32(bar), done;
+  uint32_t addr = smem_u32(bar), done, spins = 0;
+  unsigned long long t0 = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -200,6 +201,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+    // a barrier that never completes is a bug in the byte accounting: trap (the launch fails with
+    // an error the host reports) instead of spinning until someone resets the GPU
+    if (!done && (++spins & 0x3FFFu) == 0) {
+      const unsigned long long t = globaltimer_ns();
+      if (!t0) t0 = t;
+      else if (t - t0 > 4000000000ull) __trap();
+    }
   } while (!done);
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first()

@@ -260,7 +260,9 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
         int           *sii = reinterpret_cast<int *>(st + aabytes + ajbytes);
         const int      s16 = d.z & ~15;
         const int      nn8 = ((d.w + 15) & ~15) - s16;   // IDX8: bytes of codes
-        mbar_expect_tx(&full[s], (uint32_t)(nn * 8 + (IDX8 ? nn8 : nn * 4) + nr * 4));
+        // expect exactly the bytes issued below: a tile of empty rows (nn == 0) copies no codes even
+        // when the 16-byte rounding of the code range (nn8) is not empty
+        mbar_expect_tx(&full[s], (uint32_t)((nn > 0 ? nn * 8 + (IDX8 ? nn8 : nn * 4) : 0) + nr * 4));
         if (nn > 0) {
           bulk_g2s(saa, aa + s4, (uint32_t)nn * 8, &full[s], pol);
           if (IDX8) bulk_g2s(saj, ix.aj8 + s16, (uint32_t)nn8, &full[s], pol);

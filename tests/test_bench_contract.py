@@ -46,3 +46,16 @@ def test_product_arm_refuses_without_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--grid", "20", "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=120)
     assert out.returncode != 0 and "no CPU fallback" in (out.stdout + out.stderr)
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    """The reference arm must run on oracle/ alone: no libb200aij.so / libb200petsc.so in its address
+    space (the driver records which in-tree .so files each arm loads)."""
+    code = ("import sys, argparse; sys.path.insert(0, %r); import bench; "
+            "bench.run_reference(argparse.Namespace(grid=20, steps=1, warmup=1, gpus=1)); "
+            "maps = open('/proc/self/maps').read(); "
+            "assert 'libb200' not in maps, [l for l in maps.splitlines() if 'libb200' in l]; "
+            "assert 'petsc_openacc_b200' not in sys.modules; "
+            "assert 'liboracle' in maps or 'libref_matmult' in maps") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]

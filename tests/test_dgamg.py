@@ -1,8 +1,7 @@
 """Row-partitioned multigrid set-up (petsc-openacc_b200/dgamg.py, BASELINE configs[2]): every rank
 builds its rows of every level; the assembled hierarchy must equal the global restatement
 oracle/gamg.py::uncoupled_hierarchy.  All ranks run as threads of this process (ThreadComm) and, once,
-as two gloo processes (TorchComm).  The device solve of dgamg.Solver has not run on a GPU yet: its
-test is behind B200_EXPERIMENTAL=1."""
+as two gloo processes (TorchComm); the device solve with all ranks on one device is the gpu test."""
 import os
 import subprocess
 import sys
@@ -237,8 +236,6 @@ def test_solver_orchestration_with_the_oracle_backend(pk, N, size, sweeps):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL", "0") != "1",
-                    reason="dgamg.Solver has not run on a GPU yet (round-1 budget spent): B200_EXPERIMENTAL=1 enables it")
 @pytest.mark.parametrize("N,size", [(12, 2), (16, 4)])
 def test_device_solve_in_process_ranks(pk, cuda, N, size):
     """All ranks on one device (threads, split-phase halo): the CG + V-cycle solve against the C

@@ -311,6 +311,35 @@ def test_byte_codes_with_more_diagonals_than_cta_threads(pk, cuda, monkeypatch):
     A.destroy()
 
 
+@pytest.mark.parametrize("threads", ["128", "256"])
+@pytest.mark.parametrize("index8", ["1", "0"])
+def test_tiles_of_empty_rows_with_unaligned_code_offset(pk, cuda, monkeypatch, threads, index8):
+    """Regression (round-1 review): a stream tile made only of empty rows whose first non-zero
+    offset is 4 mod 16 copies no values and no codes; the producer must not make the stage's
+    barrier wait for the 16 bytes of the rounded code range (the consumers would spin for ever).
+    Rows 200..999 are empty and ai[200] = 596 = 37*16 + 4, so every tile inside that run, for both
+    CTA sizes, is such a tile."""
+    m, n = 3000, 3002
+    lens = np.full(m, 3, np.int64)
+    lens[:4] = 2
+    lens[200:1000] = 0
+    ai = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    assert ai[200] % 16 == 4 and ai[200] == ai[1000]
+    aj = np.concatenate([np.arange(r, r + lens[r]) for r in range(m)]).astype(np.int32)
+    aa = gen.uniform_pm1(len(aj), 17)
+    monkeypatch.setenv("B200_STREAM_THREADS", threads)
+    monkeypatch.setenv("B200_INDEX8", index8)
+    A = pk.Csr(ai, aj, aa, n=n)
+    info = A.info()
+    assert pk.KERNEL_NAMES[info.kernel_exact] == "stream" and (info.index8_diagonals == 3) == (index8 == "1")
+    x, y0 = gen.uniform_pm1(n, 5), gen.uniform_pm1(m, 6)
+    for mode in (pk.MODE_EXACT, pk.MODE_EXACT_FMA):
+        fma = mode != pk.MODE_EXACT
+        assert np.array_equal(_run(pk, cuda, A, x, mode), oracle.matmult(ai, aj, aa, x, fma=fma))
+        assert np.array_equal(_run(pk, cuda, A, x, mode, add=y0), oracle.matmultadd(ai, aj, aa, x, y0, fma=fma))
+    A.destroy()
+
+
 def test_compressed_index_plan_and_equivalence(pk, cuda, monkeypatch):
     """Stencil matrices stream 1-byte diagonal codes; results are the same bits as with int32
     column indices, and matrices with more than 256 diagonals keep int32."""

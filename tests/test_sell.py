@@ -4,17 +4,12 @@ stencil matrices"): b200_sell_pack / b200_csr_build_sell / B200_KERNEL_SELL.
 CPU: the host packing, checked by walking the packed arrays exactly the way k_sell does (lane l of a
 chunk reads base + 32 k + l, skips padding, adds left to right) -- the result must be the oracle's
 bits, for every sigma.
-GPU: the kernel itself against the oracle.  These were written after the round's GPU budget was
-spent, so they run only with B200_EXPERIMENTAL=1 until a GPU run has confirmed them."""
-import os
-
+GPU: the kernel itself against the oracle."""
 import numpy as np
 import pytest
 
 import gen
 import oracle
-
-EXPERIMENTAL = os.environ.get("B200_EXPERIMENTAL", "0") == "1"
 
 
 def walk_like_k_sell(m, cs, perm, val, col, x, y0=None):
@@ -94,7 +89,6 @@ def test_padding_overhead_of_the_reference_matrix(pk):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not EXPERIMENTAL, reason="k_sell has not run on a GPU yet (round-1 budget spent): B200_EXPERIMENTAL=1 enables it")
 @pytest.mark.parametrize("name", sorted(CASES))
 @pytest.mark.parametrize("sigma", [1, 64])
 def test_sell_kernel_bit_exact(pk, cuda, name, sigma):

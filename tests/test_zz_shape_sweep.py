@@ -4,9 +4,7 @@ number of distinct diagonals, emptiness and skew are drawn so that every plan br
 merge, long rows, compressed row), every operation against the oracle bit for bit.
 
 Written after the multigrid levels exposed a plan-dependent fault in k_stream (byte codes x 160-thread
-CTAs) that no hand-picked case had hit.  Added after the round's GPU budget was spent: it runs with
-B200_EXPERIMENTAL=1 until a first GPU run has confirmed it (sorted last on purpose)."""
-import os
+CTAs) that no hand-picked case had hit (sorted last on purpose)."""
 
 import numpy as np
 import pytest
@@ -14,9 +12,7 @@ import pytest
 import gen
 import oracle
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL", "0") != "1",
-                                 reason="not yet run on a GPU (round-1 budget spent): B200_EXPERIMENTAL=1 enables it")]
+pytestmark = pytest.mark.gpu
 
 
 def banded(m, n, mean, ndiag, rng, empty_frac=0.0):
