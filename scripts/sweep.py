@@ -1,5 +1,5 @@
 """Kernel sweep on one GPU: time every kernel / stream configuration on a stencil matrix.
-Usage: python scripts/sweep.py [N] [stencil=7|27]"""
+Usage: python scripts/sweep.py [N] [stencil=7|27] [quick]"""
 import os
 import sys
 import time
@@ -85,6 +85,8 @@ def main():
         report(f"sell-32-{sigma} fma", A, pk.MODE_EXACT_FMA, pk.KERNEL_SELL)
     A.destroy()
     mean = nz / m
+    if len(sys.argv) > 3 and sys.argv[3] == "quick":   # kernels only, no stream-configuration sweep
+        return
     for threads in (256, 128):
         for capmul in (1.0,):
             for stages in (1, 2, 3):

@@ -84,6 +84,65 @@ def test_port_equals_the_reference_loop_on_irregular_matrices():
         assert np.array_equal(oracle.matmultadd(ai, aj, aa, x, np.zeros(len(ai) - 1)), ref)
 
 
+def _pin_cases():
+    rng = np.random.default_rng(23)
+    p = oracle.poisson7(12)
+    return {
+        "poisson7_12": (p["ai"], p["aj"], p["aa"], 12 ** 3),
+        "stencil27_7": (*gen.stencil27(7, seed=2), 7 ** 3),
+        "powerlaw_5k": (*gen.powerlaw(5000, lmax=800), 5000),
+        "ragged_nonsquare": (*gen.random_csr(700, 500, 40, rng, empty_frac=0.3), 500),
+        "mostly_empty": (*gen.random_csr(2000, 300, 3, rng, empty_frac=0.9), 300),
+    }
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(_pin_cases()))
+def test_transpose_add_and_compressed_row_pinned_to_the_reference_loop(name):
+    """MatMultAdd / MatMultTranspose[Add] / the compressed-row branch have no text in the reference;
+    what it does hold is the MatMult row loop (oracle/_ref).  Each restatement is tied to that loop by
+    feeding it an equivalent matrix built independently (scipy):
+      * transpose: A^T as CSR with ascending columns -- row c of A^T lists column c's entries in
+        ascending row order, the order in which the scatter loop y[aj[k]] += x[i]*aa[k] adds them;
+      * add: [I | A] applied to [y; x] -- the row sum starts 0.0 + 1.0*y_i = y_i, then the same adds;
+      * compressed row: the loop over the non-empty rows only, scattered through rindex."""
+    ai, aj, aa, n = _pin_cases()[name]
+    m = len(ai) - 1
+    A = sp.csr_matrix((aa, aj, ai), shape=(m, n))
+    x, xt = gen.uniform_pm1(n, 31), gen.uniform_pm1(m, 32)
+    y0, z0 = gen.uniform_pm1(m, 33), gen.uniform_pm1(n, 34)
+    # --- transpose ---------------------------------------------------------------------------
+    T = A.T.tocsr()
+    T.sort_indices()
+    want_t = oracle.ref_matmult(T.indptr.astype(np.int32), T.indices.astype(np.int32), T.data, xt)
+    assert np.array_equal(oracle.matmulttranspose(ai, aj, aa, xt, n), want_t)
+    # --- add: [I | A] [y; x] -----------------------------------------------------------------
+    def augmented(M, rows):
+        I = sp.identity(rows, format="csr")
+        G = sp.hstack([I, M]).tocsr()
+        G.sort_indices()
+        return G.indptr.astype(np.int32), G.indices.astype(np.int32), G.data
+    gi, gj, ga = augmented(A, m)
+    assert np.array_equal(oracle.matmultadd(ai, aj, aa, x, y0), oracle.ref_matmult(gi, gj, ga, np.concatenate([y0, x])))
+    gi, gj, ga = augmented(T, n)
+    assert np.array_equal(oracle.matmulttransposeadd(ai, aj, aa, xt, z0, n), oracle.ref_matmult(gi, gj, ga, np.concatenate([z0, xt])))
+    # --- compressed row ----------------------------------------------------------------------
+    nzr = int((np.diff(ai) > 0).sum())
+    use, cpi, ridx = oracle.check_compressed_row(ai, nzr)
+    if use:
+        compact = oracle.ref_matmult(cpi, aj, aa, x)            # the loop over the non-empty rows
+        want = np.zeros(m)
+        want[ridx] = compact
+        assert np.array_equal(oracle.matmult_cprow(m, cpi, ridx, aj, aa, x), want)
+        assert np.array_equal(oracle.matmult(ai, aj, aa, x), want)
+        ci, cj, ca = augmented(sp.csr_matrix((aa, aj, cpi), shape=(len(ridx), n)), len(ridx))
+        wadd = y0.copy()
+        wadd[ridx] = oracle.ref_matmult(ci, cj, ca, np.concatenate([y0[ridx], x]))
+        assert np.array_equal(oracle.matmultadd_cprow(m, cpi, ridx, aj, aa, x, y0), wadd)
+    else:
+        assert name != "mostly_empty"
+
+
 @pytest.mark.parametrize("case", GOLD["mpi"], ids=lambda c: f"N{c['N']}x{c['size']}")
 def test_golden_mpi(case):
     N, size = case["N"], case["size"]
