@@ -13,9 +13,11 @@ import time
 import numpy as np
 
 
-def run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler, workload_config):
+def run(args, pk, B):
+    """B = the bench module (metric strings, byte formulas, clock sampler, config)."""
     import torch
     import torch.distributed as dist
+    algorithmic_bytes, measured_peak, ClockSampler = B.algorithmic_bytes, B.measured_peak, B.ClockSampler
     world = int(os.environ["WORLD_SIZE"])
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -50,6 +52,8 @@ def run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler, worklo
     nloc = M.nloc
     rows_global, nnz_global = int(base[-1]), 7 * n ** 3 - 6 * n ** 2
     nbytes = algorithmic_bytes(nnz_global, rows_global)
+    if args.workload == "cg":
+        return run_cg(args, pk, B, M, g, dev, rows_global, nnz_global)
     xg = pk.gen_vector(rows_global, 0xB200)
     hx, hy = pk.PinnedArray(nloc), pk.PinnedArray(nloc)
     hx.array[:] = xg[base[rank]:base[rank + 1]]
@@ -166,15 +170,16 @@ def run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler, worklo
         peak, peak_src = measured_peak()
         value = nbytes / ms / 1e6
         line = {
-            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "metric": B.workload_metric(args), "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "gflops": 2.0 * nnz_global / ms / 1e6,
-            "config": workload_config(n, world, rows_global, nnz_global),
+            "config": B.workload_config(args, rows_global, nnz_global),
             "plan": {"mode": args.mode, "halo": halo, "process_grid": [int(v) for v in g["info"][:3]],
                      "rows_per_rank": nloc, "nghost_rank0": M.nghost, "parity_vs_oracle": parity},
             "roofline": {"bound": "hbm", "achieved": value / world, "peak": peak, "unit": "GB/s",
-                         "frac": value / world / peak, "traffic": None, "kernel": "k_stream (diagonal block) + k_halo_push + k_offdiag",
+                         "frac": value / world / peak, "traffic": B.ncu_traffic(f"dram_bytes_per_launch_halo_{world}"),
+                         "kernel": "k_stream<HALO> (one fused launch per rank: NVLink push + A x + ghost rows)",
                          "peak_source": peak_src, "note": "per-GPU share of the whole-job rate, halo and launches included"},
             "nccl_halo": {"ms_per_step": ms_nccl, "value": nbytes / ms_nccl / 1e6, "unit": "GB/s",
                           "note": "same pack/off-diagonal kernels, torch.distributed batch_isend_irecv transport"},
@@ -182,6 +187,61 @@ def run(args, pk, METRIC, algorithmic_bytes, measured_peak, ClockSampler, worklo
                     "h2d_bytes_per_step": rows_global * 8, "d2h_bytes_per_step": rows_global * 8,
                     "steps": e2e_steps, "api": "b200_mpiaij_mult_host (MatMult_MPIAIJ with host Vecs, pinned)" if use_p2p else "host rows up + NCCL-transport MatMult + rows down"},
             "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    M.destroy()
+    dist.destroy_process_group()
+    return 0
+
+
+def run_cg(args, pk, B, M, g, dev, rows_global, nnz_global):
+    """`steps` iterations of KSPCG + PCJACOBI on the row-partitioned matrix (b200_mpiaij_cg_jacobi):
+    fused MatMult_MPIAIJ with (p, A p) folded in, all-reduces over the peer windows, no host sync."""
+    import torch
+    import torch.distributed as dist
+    world, rank = M.size, M.rank
+    handles = [None] * world
+    dist.all_gather_object(handles, M.ipc_handle())
+    for q in range(world):
+        M.set_rank_window(q, handle=handles[q] if q != rank else None)
+    gv = pk.gen_poisson7(args.grid, world, rank, vectors=True)
+    b = torch.from_numpy(gv["rhs"]).to(dev)
+    x = torch.zeros(M.nloc, dtype=torch.float64, device=dev)
+    mode = {"fast": pk.MODE_FAST, "exact": pk.MODE_EXACT, "exact_fma": pk.MODE_EXACT_FMA}[args.mode]
+    warm = max(args.warmup, 3)
+    M.cg_jacobi(b, x, rtol=1e-30, atol=1e-300, max_it=warm, mode=mode)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = B.ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    res = M.cg_jacobi(b, x, rtol=1e-30, atol=1e-300, max_it=args.steps, mode=mode)
+    M.check()
+    t = torch.tensor([res.solve_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    its = torch.tensor([res.its], device=dev)
+    dist.all_reduce(its, op=dist.ReduceOp.MIN)
+    ms = float(t.item()) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        nbytes = B.cg_bytes(nnz_global, rows_global)
+        peak, peak_src = B.measured_peak()
+        line = {
+            "metric": B.workload_metric(args), "value": nbytes / ms / 1e6, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(B.workload_config(args, rows_global, nnz_global), bytes_per_iteration=int(nbytes)),
+            "plan": {"mode": args.mode, "launches_per_iteration": res.launches / max(res.its, 1),
+                     "iterations_done_min_over_ranks": int(its.item()), "process_grid": [int(v) for v in g["info"][:3]]},
+            "roofline": {"bound": "hbm", "achieved": nbytes / ms / 1e6 / world, "peak": peak, "unit": "GB/s",
+                         "frac": nbytes / ms / 1e6 / world / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_cg_p + k_stream<EPI_DOT,HALO> + k_allreduce + k_cg_r + k_allreduce",
+                         "note": "per-GPU share; bytes = MatMult algorithmic bytes + 10 vector passes"},
+            "cpu_baseline": None,
+            "e2e": {"value": nbytes / ms / 1e6, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "device-resident solve; see the matmult workload for the host-vector path"},
+            "gpu_launches": int(res.launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

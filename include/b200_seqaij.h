@@ -213,6 +213,11 @@ int b200_gen_powerlaw_rowptr(int32_t m, int32_t n, double alpha, int32_t lmax, u
 int b200_gen_powerlaw_fill(int32_t m, int32_t n, double alpha, int32_t lmax, uint64_t seed,
                            const int32_t *ai, int32_t *aj, double *aa);
 
+/* BASELINE configs[3]: 27-point box stencil on an N^3 grid (non-periodic, natural ordering, nnz =
+ * (3N-2)^3): off-diagonal -1, diagonal = number of neighbours, or uniform [-1,1) values when seed != 0.
+ * ai[N^3 + 1] is always filled; aj / aa may be NULL for a sizing call.                               */
+int b200_gen_stencil27(int32_t N, uint64_t seed, int32_t *ai, int32_t *aj, double *aa);
+
 #ifdef __cplusplus
 }
 #endif

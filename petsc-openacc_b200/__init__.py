@@ -454,7 +454,17 @@ def gen_poisson7(M, size=1, rank=0, refpoint=True, vectors=False):
 
 
 ABI_SYMBOLS += ["b200_gen_poisson7_info", "b200_gen_poisson7_bases", "b200_gen_poisson7",
-                "b200_gen_powerlaw_rowptr", "b200_gen_powerlaw_fill"]
+                "b200_gen_powerlaw_rowptr", "b200_gen_powerlaw_fill", "b200_gen_stencil27"]
+
+
+def gen_stencil27(N, seed=0):
+    """The 27-point matrix of BASELINE configs[3] from the product generator (threaded C++)."""
+    n = N ** 3
+    ai = np.zeros(n + 1, np.int32)
+    check(lib.b200_gen_stencil27(C.c_int32(N), C.c_uint64(seed), _np_ptr(ai), None, None))
+    aj, aa = np.zeros(int(ai[-1]), np.int32), np.zeros(int(ai[-1]))
+    check(lib.b200_gen_stencil27(C.c_int32(N), C.c_uint64(seed), _np_ptr(ai), _np_ptr(aj), _np_ptr(aa)))
+    return ai, aj, aa
 
 
 def gen_powerlaw(m, n=None, alpha=2.0, lmax=10000, seed=0x5EED):

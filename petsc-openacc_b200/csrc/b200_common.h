@@ -27,8 +27,23 @@ extern std::atomic<uint64_t>    g_launches;
 
 int  set_error(int code, const char *fmt, ...);
 int  ensure_device();        // B200_OK when an sm_100 device is current
-int  sm_count();
+int  sm_count();             // of the current device
 int  env_int(const char *name, int dflt);
+
+// State that belongs to one device (the process may drive several): capability check, SM count, the
+// "opt-in shared memory limit raised" latch of the stream kernels (cudaFuncSetAttribute is per
+// device), and the reduction scratch (one slot per stream: reductions on one stream are ordered,
+// reductions on different streams never share partial sums).
+struct RedSlot {
+  double   *partials = nullptr;   // 2 * RED_MAX_GRID
+  unsigned *counter  = nullptr;
+};
+struct DeviceState {
+  int  ordinal = -1, sm_count = 0;
+  bool checked = false, ok = false, stream_attrs_set = false;
+};
+DeviceState *device_state();                        // of the current device; nullptr on failure (error set)
+int red_slot_for(cudaStream_t st, RedSlot *out);    // b200_vec.cu
 
 #define B200_CUDA_TRY(expr)                                                                    \
   do {                                                                                         \
@@ -51,6 +66,28 @@ int  env_int(const char *name, int dflt);
     b200::g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
     B200_CUDA_TRY(cudaGetLastError());                                                         \
   } while (0)
+
+// Programmatic dependent launch: the kernel may become resident while the previous kernel of the
+// stream is still draining; everything it does before `griddepcontrol.wait` (shared-memory set-up,
+// mbarrier init, the first bulk copies of the CONSTANT matrix arrays) overlaps that tail.  Only for
+// kernels that execute pdl_wait() before touching anything an earlier kernel wrote.
+// B200_PDL=0 launches them the ordinary way (A/B measurements).
+#define B200_LAUNCH_PDL(kernel, grid_, block_, smem_, stream_, ...)                            \
+  do {                                                                                         \
+    cudaLaunchConfig_t    cfg_{};                                                              \
+    cudaLaunchAttribute   att_[1];                                                             \
+    cfg_.gridDim = dim3(grid_); cfg_.blockDim = dim3(block_);                                  \
+    cfg_.dynamicSmemBytes = (smem_); cfg_.stream = (stream_);                                  \
+    att_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                           \
+    att_[0].val.programmaticStreamSerializationAllowed = 1;                                    \
+    cfg_.attrs = att_; cfg_.numAttrs = b200::pdl_enabled() ? 1 : 0;                            \
+    cudaError_t le_ = cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                          \
+    b200::g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+    if (le_ != cudaSuccess)                                                                    \
+      return b200::set_error(B200_ERR_CUDA, "%s:%d launch of %s -> %s", __FILE__, __LINE__,    \
+                             #kernel, cudaGetErrorString(le_));                                \
+  } while (0)
+bool pdl_enabled();
 
 // ---------------------------------------------------------------------------------------------
 // Halo pieces shared by b200_halo.cu (owner) and the fused stream kernel in b200_spmv.cu.
@@ -83,13 +120,31 @@ struct HaloArgs {
   unsigned long long *err;
   unsigned long long  timeout_ns;
 };
+// MatMult with CG's (p, A p) folded into its epilogue (k_stream, EPI_DOT): every CTA leaves one
+// partial sum, the last CTA to finish adds them in index order -> *out (deterministic for a plan).
+// skip != nullptr and *skip != 0: the launch does nothing (the solve has converged on the device
+// and the remaining launches of the chunk drain).
+struct DotArgs {
+  double    *partials = nullptr;  // one per CTA of the stream grid
+  unsigned  *counter  = nullptr;
+  double    *out      = nullptr;
+  const int *skip     = nullptr;
+};
+// CG scalars and state words in device memory (b200_vec.cu, also finished by k_allreduce)
+enum { CG_BETA = 0, CG_BETAOLD = 1, CG_DPI = 2, CG_DP = 3, CG_A = 4, CG_ZZ = 5, CG_ZR = 6, CG_TTOL = 7,
+       CG_RNORM0 = 8, CG_RTOL = 9, CG_ATOL = 10, CG_NSCAL = 16 };
+enum { CGI_ITS = 0, CGI_REASON = 1, CGI_DONE = 2, CGI_MAXIT = 3, CGI_NINT = 4 };
+enum { CG_POST_NONE = 0, CG_POST_BEGIN = 1, CG_POST_ROTATE = 2 };
 // the CG body shared by b200_cg_jacobi and b200_mpiaij_cg_jacobi (b200_vec.cu)
 struct CgOps {
   int            m = 0;                       // local rows
   const int32_t *ai = nullptr, *aj = nullptr; // diagonal block (for PCJACOBI)
   const double  *aa = nullptr;
-  std::function<int(const double *, double *, cudaStream_t)> mult;       // w = A p
-  std::function<int(double *, int, cudaStream_t)>            allreduce;  // in place, device scalars; empty on one GPU
+  int            dot_partials = 0;            // partial sums mult_dot needs (0: it reduces by itself)
+  // w = A p and dot.out = (p, w) over the local rows
+  std::function<int(const double *, double *, const DotArgs &, cudaStream_t)> mult_dot;
+  // in place sum over the ranks of n device scalars, then the scalar step `post` on sc/st; empty on one GPU
+  std::function<int(double *, int, int post, double *sc, int *st, cudaStream_t)> allreduce;
 };
 int cg_jacobi_run(const CgOps &ops, const double *d_b, double *d_x, double rtol, double atol,
                   int32_t max_it, b200_cg_result_t *res, cudaStream_t st);
@@ -97,9 +152,44 @@ int cg_jacobi_run(const CgOps &ops, const double *d_b, double *d_x, double rtol,
 // internal (not part of the C ABI): the stream plan of a matrix and the fused launch
 int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid, int *threads);   // 0 tiles = not applicable
 int launch_stream_halo(b200_csr_t A, const double *x, double *y, int mode, const HaloArgs &h,
-                       cudaStream_t st);
+                       cudaStream_t st, const DotArgs *dot = nullptr);
+int stream_grid_of(b200_csr_t A);   // CTAs of the stream launch (0: the plan is not the stream kernel)
+// w = A x with (x, w) folded in when the plan is the stream kernel, else MatMult + a reduction
+int spmv_dot(b200_csr_t A, const double *x, double *y, int mode, const DotArgs &dot, cudaStream_t st);
 
 #ifdef __CUDACC__
+// The scalar steps of KSPSolve_CG [P376] (one thread): after the first (z,z), (z,r) ...
+__device__ __forceinline__ void cg_scalar_converged(double dp, double *sc, int *st)
+{
+  if (!(dp == dp)) { st[CGI_REASON] = -9; st[CGI_DONE] = 1; }               // KSP_DIVERGED_NANORINF
+  else if (dp < sc[CG_TTOL]) { st[CGI_REASON] = (dp < sc[CG_ATOL]) ? 3 : 2; st[CGI_DONE] = 1; }
+  else if (st[CGI_ITS] >= st[CGI_MAXIT]) { st[CGI_REASON] = -3; st[CGI_DONE] = 1; }   // KSP_DIVERGED_ITS
+}
+__device__ __forceinline__ void cg_scalar_begin(double *sc, int *st)
+{
+  const double dp = sqrt(sc[CG_ZZ]);
+  sc[CG_DP] = dp; sc[CG_RNORM0] = dp; sc[CG_BETA] = sc[CG_ZR];
+  sc[CG_TTOL] = fmax(sc[CG_RTOL] * dp, sc[CG_ATOL]);
+  st[CGI_ITS] = 0;
+  cg_scalar_converged(dp, sc, st);
+}
+// ... and after each iteration's (z,z), (z,r): dp = ||z||, betaold <- beta <- (z,r), a kept for the
+// deferred x update, iteration count, convergence test (KSPConvergedDefault)
+__device__ __forceinline__ void cg_scalar_rotate(double *sc, int *st)
+{
+  const double dp = sqrt(sc[CG_ZZ]);
+  sc[CG_A]       = sc[CG_BETA] / sc[CG_DPI];
+  sc[CG_DP]      = dp;
+  sc[CG_BETAOLD] = sc[CG_BETA];
+  sc[CG_BETA]    = sc[CG_ZR];
+  st[CGI_ITS] += 1;
+  cg_scalar_converged(dp, sc, st);
+}
+__device__ __forceinline__ void cg_scalar_post(int post, double *sc, int *st)
+{
+  if (post == CG_POST_BEGIN) cg_scalar_begin(sc, st);
+  else if (post == CG_POST_ROTATE) cg_scalar_rotate(sc, st);
+}
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -116,19 +206,28 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// programmatic dependent launch (see B200_LAUNCH_PDL): let the next kernel of the stream start its
+// prologue; wait until everything earlier kernels wrote is visible
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // the push role: gather x[send_idx] into the peer's lvec over NVLink; the last CTA of a peer
 // releases that peer's flag
+// NT > 0: only the first NT threads of the CTA take part (the consumer threads of k_stream; they
+// meet on named barrier 1); NT == 0: the whole CTA.
+template <int NT>
 __device__ __forceinline__ void halo_push_block(const HaloArgs &h, const double *__restrict__ x, int block)
 {
   const PushBlock b   = h.blocks[block];
   const PushPeer  p   = h.peers[b.peer_slot];
   double         *dst = p.dst[h.seq & 1];
-  for (int t = threadIdx.x; t < b.count; t += blockDim.x) {
+  const int       nt  = NT > 0 ? NT : (int)blockDim.x;
+  for (int t = threadIdx.x; t < b.count; t += nt) {
     const int e = b.start + t;
     dst[e]      = __ldg(x + h.send_idx[e]);
   }
   __threadfence_system();
-  __syncthreads();
+  if (NT > 0) asm volatile("bar.sync 1, %0;" ::"n"(NT > 0 ? NT : 32) : "memory");
+  else __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned prev = atomicAdd(h.done + b.peer_slot, 1u);
     if (prev == (unsigned)p.nblocks - 1) {

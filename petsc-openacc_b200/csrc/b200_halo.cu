@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256)
 {
   HaloArgs h{};
   h.blocks = blocks; h.peers = peers; h.send_idx = send_idx; h.done = done; h.seq = seq;
-  halo_push_block(h, x, blockIdx.x);
+  halo_push_block<0>(h, x, blockIdx.x);
 }
 
 // pack only (transport owned by the caller)
@@ -85,19 +85,26 @@ __global__ void __launch_bounds__(128)
 // then reads all slots of its own window and adds them in rank order -- every rank gets the same
 // bits.  Slots alternate with the sequence number; a rank can be at most one all-reduce ahead of
 // a peer, so two slots per source are enough.  One CTA, one lane per rank.
-struct RedSlot { double v[3]; unsigned long long seq; };
+// CG rides on it: `skip` (the solve's DONE word, identical on every rank because it is computed from
+// all-reduced values) turns the launch into a no-op, and `post` runs the scalar step of the
+// iteration (b200_common.h) on the reduced values -- one launch instead of all-reduce + scalar kernel.
+struct WinSlot { double v[3]; unsigned long long seq; };
 __global__ void __launch_bounds__(128)
     k_allreduce(double *vals, int nvals, int size, int rank, unsigned char *const *windows,
-                unsigned long long seq, unsigned long long *err, unsigned long long timeout_ns)
+                unsigned long long seq, unsigned long long *err, unsigned long long timeout_ns,
+                const int *skip, int post, double *sc, int *st)
 {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (skip && *skip) return;
   __shared__ double sv[MAX_RANKS][RED_MAX_VALS];
   const int t = threadIdx.x;
   if (t < size) {
-    RedSlot *dst = reinterpret_cast<RedSlot *>(windows[t] + RED_SLOT_OFFSET) + (seq & 1) * MAX_RANKS + rank;
+    WinSlot *dst = reinterpret_cast<WinSlot *>(windows[t] + RED_SLOT_OFFSET) + (seq & 1) * MAX_RANKS + rank;
     for (int k = 0; k < nvals; ++k) dst->v[k] = vals[k];
     __threadfence_system();
     st_release_sys(&dst->seq, seq);
-    const RedSlot *src = reinterpret_cast<const RedSlot *>(windows[rank] + RED_SLOT_OFFSET) + (seq & 1) * MAX_RANKS + t;
+    const WinSlot *src = reinterpret_cast<const WinSlot *>(windows[rank] + RED_SLOT_OFFSET) + (seq & 1) * MAX_RANKS + t;
     const unsigned long long t0 = globaltimer_ns();
     while (ld_relaxed_sys(&src->seq) < seq) {
       if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(err, 1ull); break; }
@@ -111,6 +118,10 @@ __global__ void __launch_bounds__(128)
     double s = 0.0;
     for (int q = 0; q < size; ++q) s += sv[q][t];
     vals[t] = s;
+  }
+  if (post) {
+    __syncthreads();
+    if (t == 0) cg_scalar_post(post, sc, st);
   }
 }
 
@@ -508,16 +519,16 @@ extern "C" int b200_mpiaij_mult_finish(b200_mpiaij_t M, const double *d_x, doubl
   return b200_mpiaij_mult_end(M, d_y, mode, stream);
 }
 
-extern "C" int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream)
+static int mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream, const DotArgs *dot)
 {
   NvtxRange nvtx_("b200_mpiaij_mult");
   if (!M || !M->uploaded) return set_error(B200_ERR_STATE, "b200_mpiaij_upload first");
   cudaStream_t st = (cudaStream_t)stream;
   B200_TRY(prepare_push(M));
   if (M->fused_ok && M->npush_blocks <= M->fused_grid) {
-    // one launch: push prologue + A x + B lvec (k_stream<..., HALO>)
+    // one launch: push prologue + A x + B lvec (k_stream<..., HALO>), optionally (x, y) too
     M->seq += 1;
-    return launch_stream_halo(M->A, d_x, d_y, mode, fused_args(M, true), st);
+    return launch_stream_halo(M->A, d_x, d_y, mode, fused_args(M, true), st, dot);
   }
   if (M->npush_blocks) {
     // fork: the push runs beside A x; join so that the caller may overwrite x afterwards
@@ -531,7 +542,16 @@ extern "C" int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y,
   B200_TRY(b200_mpiaij_mult_local(M, d_x, d_y, mode, st));
   B200_TRY(b200_mpiaij_mult_end(M, d_y, mode, st));
   if (M->npush_blocks) B200_CUDA_TRY(cudaStreamWaitEvent(st, M->ev_join, 0));
+  if (dot) {
+    // the two-kernel path reduces after the fact
+    B200_TRY(b200_vec_dot(d_x, d_y, M->nloc, dot->out, stream));
+  }
   return B200_OK;
+}
+
+extern "C" int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y, int mode, void *stream)
+{
+  return mpiaij_mult(M, d_x, d_y, mode, stream, nullptr);
 }
 
 // MatMult_MPIAIJ(Mat,Vec,Vec) with host Vecs: upload this rank's x rows, multiply, download y.
@@ -607,7 +627,7 @@ extern "C" int b200_mpiaij_set_rank_window(b200_mpiaij_t M, int32_t q, const voi
   return B200_OK;
 }
 
-extern "C" int b200_mpiaij_allreduce_sum(b200_mpiaij_t M, double *d_vals, int32_t nvals, void *stream)
+static int allreduce_sum(b200_mpiaij_t M, double *d_vals, int32_t nvals, const int *skip, int post, double *sc, int *sti, void *stream)
 {
   NvtxRange nvtx_("b200_mpiaij_allreduce_sum");
   if (!M || !M->uploaded || !d_vals || nvals < 1 || nvals > RED_MAX_VALS) return set_error(B200_ERR_ARG, "b200_mpiaij_allreduce_sum: bad argument");
@@ -620,9 +640,15 @@ extern "C" int b200_mpiaij_allreduce_sum(b200_mpiaij_t M, double *d_vals, int32_
     B200_TRY(up(&M->d_all_windows, M->all_windows));
   }
   M->rseq += 1;
-  B200_LAUNCH(k_allreduce, 1, 128, 0, (cudaStream_t)stream, d_vals, nvals, M->size, M->rank, M->d_all_windows, M->rseq,
-              (unsigned long long *)M->d_window + ERR_WORD, M->timeout_ns);
+  B200_LAUNCH_PDL(k_allreduce, 1, 128, 0, (cudaStream_t)stream, d_vals, (int)nvals, (int)M->size, (int)M->rank,
+                  (unsigned char *const *)M->d_all_windows, M->rseq, (unsigned long long *)M->d_window + ERR_WORD, M->timeout_ns,
+                  skip, post, sc, sti);
   return B200_OK;
+}
+
+extern "C" int b200_mpiaij_allreduce_sum(b200_mpiaij_t M, double *d_vals, int32_t nvals, void *stream)
+{
+  return allreduce_sum(M, d_vals, nvals, nullptr, CG_POST_NONE, nullptr, nullptr, stream);
 }
 
 // KSPCG + PCJACOBI on the row-partitioned matrix: MatMult_MPIAIJ (one fused launch) + the vector
@@ -635,8 +661,15 @@ extern "C" int b200_mpiaij_cg_jacobi(b200_mpiaij_t M, const double *d_b, double 
   CgOps ops;
   ops.m = M->nloc;
   B200_TRY(b200_csr_device_arrays(M->A, &ops.ai, &ops.aj, &ops.aa));
-  ops.mult = [M, mode](const double *p, double *w, cudaStream_t s) { return b200_mpiaij_mult(M, p, w, mode, s); };
-  if (M->size > 1) ops.allreduce = [M](double *v, int n, cudaStream_t s) { return b200_mpiaij_allreduce_sum(M, v, n, s); };
+  if (mode == B200_MODE_FAST) mode = B200_MODE_EXACT_FMA;
+  B200_TRY(prepare_push(M));
+  const bool fused = M->fused_ok && M->npush_blocks <= M->fused_grid;
+  ops.dot_partials = fused ? M->fused_grid : 0;
+  ops.mult_dot = [M, mode](const double *p, double *w, const DotArgs &dot, cudaStream_t s) { return mpiaij_mult(M, p, w, mode, s, &dot); };
+  if (M->size > 1)
+    ops.allreduce = [M](double *v, int n, int post, double *sc, int *sti, cudaStream_t s) {
+      return allreduce_sum(M, v, n, sti + CGI_DONE, post, sc, sti, s);
+    };
   B200_TRY(cg_jacobi_run(ops, d_b, d_x, rtol, atol, max_it, res, (cudaStream_t)stream));
   return b200_mpiaij_check(M);
 }

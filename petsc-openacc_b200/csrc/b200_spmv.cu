@@ -27,6 +27,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -39,6 +40,7 @@
 namespace b200 {
 
 thread_local std::string g_last_error;
+static thread_local int  g_last_code = 0;
 std::atomic<uint64_t>    g_launches{0};
 
 int set_error(int code, const char *fmt, ...)
@@ -49,6 +51,7 @@ int set_error(int code, const char *fmt, ...)
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   g_last_error = buf;
+  g_last_code  = code;
   return code;
 }
 
@@ -65,29 +68,56 @@ NvtxRange::NvtxRange(const char *name)
   if (on) nvtxRangePushA(name);
 }
 
-static int g_sm_count = 0;
-static int g_dev_ok   = -1;
+static DeviceState g_devs[64];
+static std::mutex  g_dev_mutex;
 
-int ensure_device()
+DeviceState *device_state()
 {
-  if (g_dev_ok == 1) return B200_OK;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
     cudaGetLastError();
-    return set_error(B200_ERR_NO_DEVICE, "no CUDA device visible: the b200 library has no CPU fallback");
+    set_error(B200_ERR_NO_DEVICE, "no CUDA device visible: the b200 library has no CPU fallback");
+    return nullptr;
   }
   int dev = 0;
-  B200_CUDA_TRY(cudaGetDevice(&dev));
-  cudaDeviceProp p;
-  B200_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
-  if (p.major != 10)
-    return set_error(B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
-                     dev, p.major, p.minor);
-  g_sm_count = p.multiProcessorCount;
-  g_dev_ok   = 1;
-  return B200_OK;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    set_error(B200_ERR_CUDA, "cudaGetDevice failed or device ordinal out of range");
+    return nullptr;
+  }
+  DeviceState *d = &g_devs[dev];
+  if (!d->checked) {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    if (!d->checked) {
+      cudaDeviceProp p;
+      if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        set_error(B200_ERR_CUDA, "cudaGetDeviceProperties(%d) failed", dev);
+        return nullptr;
+      }
+      d->ordinal  = dev;
+      d->sm_count = p.multiProcessorCount;
+      d->ok       = (p.major == 10);
+      if (!d->ok) d->sm_count = p.major * 10 + p.minor;   // kept for the message below
+      d->checked  = true;
+    }
+  }
+  if (!d->ok) {
+    set_error(B200_ERR_NO_DEVICE, "device %d is sm_%d; this library is built for sm_100a only", dev, d->sm_count);
+    return nullptr;
+  }
+  return d;
 }
-int sm_count() { return g_sm_count; }
+
+int ensure_device() { return device_state() ? B200_OK : g_last_code; }
+int sm_count()
+{
+  DeviceState *d = device_state();
+  return d ? d->sm_count : 0;
+}
+bool pdl_enabled()
+{
+  static const bool on = env_int("B200_PDL", 1) != 0;
+  return on;
+}
 
 }  // namespace b200
 
@@ -196,19 +226,20 @@ __host__ __device__ inline size_t stream_header_bytes(bool idx8) { return idx8 ?
 //   3  y_i = x_i + dinv_i * (b_i - t_i)   one Richardson(1) + PCJACOBI sweep of the GAMG levels
 //      (configs/PETSc_SolverOptions_GAMG.info:15-21), i.e. MatMult, VecAYPX, VecPointwiseMult and
 //      VecAXPY in one pass; every step is rounded separately, as the four PETSc calls round.
-enum { EPI_NONE = 0, EPI_ADD = 1, EPI_RESIDUAL = 2, EPI_JACOBI = 3 };
+//   4  y_i = t_i and the CTA accumulates x_i * t_i: CG's (p, A p) without a second pass over p and w
+enum { EPI_NONE = 0, EPI_ADD = 1, EPI_RESIDUAL = 2, EPI_JACOBI = 3, EPI_DOT = 4 };
 
 template <int MODE, int EPI, int THREADS, bool HALO, bool IDX8>
 __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     k_stream(const int4 *__restrict__ tiles, int ntiles, const int *__restrict__ ii,
              const int *__restrict__ aj, const double *__restrict__ aa,
              const double *__restrict__ x, const double *yin, double *y, int cap, int stages,
-             const HaloArgs h, const Idx8Args ix, const double *__restrict__ aux)
+             const HaloArgs h, const Idx8Args ix, const double *__restrict__ aux, const DotArgs dot)
 {
   // HALO = MatMult_MPIAIJ in one launch:
-  //  * VecScatterBegin: the first h.npush CTAs (at most one per SM) start by storing a block of this
-  //    rank's boundary values into a peer's lvec over NVLink and, once a peer's last block is out,
-  //    releasing that peer's flag; then they stream tiles like every other CTA;
+  //  * VecScatterBegin: the consumers of the first h.npush CTAs (at most one per SM) start by storing a
+  //    block of this rank's boundary values into a peer's lvec over NVLink and, once a peer's last block
+  //    is out, releasing that peer's flag; then they stream tiles like every other CTA;
   //  * VecScatterEnd + MatMultAdd(B, lvec, y, y): after its last tile a CTA waits for the flags of
   //    this rank's sources (the ghosts arrived long ago: the wait is off the critical path) and
   //    continues the rows of its own tiles that touch a ghost -- A terms first, then B terms, the
@@ -216,9 +247,14 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
   // Measured alternatives (profiles/r01_fused_halo_notes.md): folding the ghost terms into the tile
   // loop behind a per-tile bit mask, a separate communication warp, spreading the push over every
   // CTA -- all slower than this arrangement.
+  //
+  // Programmatic dependent launch: the matrix arrays (tiles, ii, aj/codes, aa, the diagonal table) are
+  // constant for the life of the handle, so the shared-memory set-up and the producer's first bulk
+  // copies run BEFORE griddepcontrol.wait, i.e. under the tail of the previous kernel of the stream;
+  // only the consumers (x, yin, y, the halo) wait for it.
+  pdl_launch_dependents();
   const int bid = (int)blockIdx.x;
   const int nb  = (int)gridDim.x;
-  if (HALO && bid < h.npush) halo_push_block(h, x, bid);
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full  = reinterpret_cast<uint64_t *>(smem);
   uint64_t *empty = full + stages;
@@ -232,14 +268,21 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     // all 256 table entries, also when the CTA has fewer than 256 threads (THREADS = 128 -> 160)
     for (int t = tid; t < 256; t += THREADS + 32) soffs[t] = __ldg(ix.offs + t);
   }
+  int *sskip = reinterpret_cast<int *>(smem + 120);             // EPI_DOT: "this launch is a no-op"
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], THREADS / 32);
     }
     mbar_fence_init();
+    // The skip word is read BEFORE griddepcontrol.wait, once per CTA.  Every CTA of the launch reads
+    // the same value because the word is only written by a scalar step at least two kernels back in
+    // the stream and the kernel in between triggers its dependents after its own wait (see
+    // cg_jacobi_run): that scalar step has completed before any CTA of this launch starts.
+    if (EPI == EPI_DOT) *sskip = (dot.skip != nullptr) ? *reinterpret_cast<const volatile int *>(dot.skip) : 0;
   }
   __syncthreads();
+  if (EPI == EPI_DOT && *sskip) return;
 
   if (tid >= THREADS) {
     // ------------------------------- producer warp -------------------------------------------
@@ -275,6 +318,9 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
   }
 
   // --------------------------------- consumers -------------------------------------------------
+  pdl_wait();
+  if (HALO && bid < h.npush) halo_push_block<THREADS>(h, x, bid);
+  double dacc = 0.0;
   int it = 0;
   for (int tile = bid; tile < ntiles; tile += nb, ++it) {
     const int  s = it % stages;
@@ -288,7 +334,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     double sum = 0.0;
     double bi = 0.0;
     if (EPI == EPI_ADD) { if (r < d.y) sum = yin[r]; }
-    if (EPI >= EPI_RESIDUAL) { if (r < d.y) bi = yin[r]; }
+    if (EPI == EPI_RESIDUAL || EPI == EPI_JACOBI) { if (r < d.y) bi = yin[r]; }
     mbar_wait(&full[s], (it / stages) & 1);
     if (r < d.y) {
       const int lo = sii[tid], hi = sii[tid + 1];
@@ -310,6 +356,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
       }
       if (EPI == EPI_RESIDUAL) sum = __dsub_rn(bi, sum);
       if (EPI == EPI_JACOBI) sum = __dadd_rn(__ldg(x + r), __dmul_rn(__ldg(aux + r), __dsub_rn(bi, sum)));
+      if (EPI == EPI_DOT) dacc = __fma_rn(__ldg(x + r), sum, dacc);
       y[r] = sum;
     }
     __syncwarp();
@@ -330,9 +377,41 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     for (int q = h.cta_ptr[bid] + tid; q < h.cta_ptr[bid + 1]; q += THREADS) {
       const int c  = h.cta_rows[q];
       const int lo = h.cpi[c], hi = h.cpi[c + 1], i = h.ridx[c];
-      double    sb = y[i];
+      const double s0 = y[i];
+      double    sb = s0;
       for (int k = lo; k < hi; ++k) sb = acc<MODE>(sb, h.ba[k], __ldcg(h.lvec + h.bj[k]));
       y[i] = sb;
+      if (EPI == EPI_DOT) dacc = __fma_rn(__ldg(x + i), __dsub_rn(sb, s0), dacc);   // the ghost terms' share of (x, y)
+    }
+  }
+  if (EPI == EPI_DOT) {
+    // CTA sum in a fixed order (lanes by butterfly, warps in index order), one partial per CTA; the
+    // last CTA to arrive adds the partials in index order: the same bits from run to run
+    double *red = reinterpret_cast<double *>(stage0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, off);
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");   // every consumer is done with the stages
+    if ((tid & 31) == 0) red[tid >> 5] = dacc;
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+    if (tid < 32) {
+      int last = 0;
+      if (tid == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) t += red[w];
+        dot.partials[bid] = t;
+        __threadfence();
+        last = (atomicAdd(dot.counter, 1u) == (unsigned)nb - 1);
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence();
+        double t = 0.0;
+        for (int q = tid; q < nb; q += 32) t += __ldcg(dot.partials + q);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (tid == 0) { *dot.out = t; *dot.counter = 0u; }
+      }
     }
   }
 }
@@ -751,48 +830,43 @@ static int dev_alloc(T **p, size_t count, b200_csr_s *A)
 template <int THREADS>
 static int stream_occupancy(size_t smem, int *ctas)
 {
-  auto kern = k_stream<B200_MODE_EXACT_FMA, false, THREADS, false, false>;  // any instantiation: same footprint
+  auto kern = k_stream<B200_MODE_EXACT_FMA, EPI_NONE, THREADS, false, false>;  // the footprint every instantiation is bounded to
   B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, kern, THREADS + 32, smem));
   return B200_OK;
 }
 
-template <int MODE, bool ADD, int THREADS>
+template <int MODE, int THREADS>
 static int stream_set_attr(size_t smem)
 {
-  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, ADD, THREADS, false, false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, ADD, THREADS, false, true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // the fused residual / Jacobi-sweep epilogues (EPI 2, 3) ride on the ADD = false pass
-  if (!ADD) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, 2, THREADS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, 2, THREADS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, 3, THREADS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, 3, THREADS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, false, THREADS, true, false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, false, THREADS, true, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+#define B200_SET(EPI_, HALO_, I8_)                                                                  \
+  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, EPI_, THREADS, HALO_, I8_>,                      \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+  B200_SET(EPI_NONE, false, false);     B200_SET(EPI_NONE, false, true);
+  B200_SET(EPI_ADD, false, false);      B200_SET(EPI_ADD, false, true);
+  B200_SET(EPI_RESIDUAL, false, false); B200_SET(EPI_RESIDUAL, false, true);
+  B200_SET(EPI_JACOBI, false, false);   B200_SET(EPI_JACOBI, false, true);
+  B200_SET(EPI_DOT, false, false);      B200_SET(EPI_DOT, false, true);
+  B200_SET(EPI_NONE, true, false);      B200_SET(EPI_NONE, true, true);
+  B200_SET(EPI_DOT, true, false);       B200_SET(EPI_DOT, true, true);
+#undef B200_SET
   return B200_OK;
 }
 
-// The opt-in limit is a per-function, process-wide attribute: raise it once to the architectural
-// maximum so that matrices with different stage sizes can coexist.
+// The opt-in limit is a per-function, PER-DEVICE attribute: raise it once on each device the process
+// uses, to the architectural maximum, so that matrices with different stage sizes can coexist.
 static int stream_set_all_attrs(int /*threads*/, size_t /*smem*/)
 {
-  static bool done = false;
-  if (done) return B200_OK;
+  DeviceState *d = device_state();
+  if (!d) return B200_ERR_NO_DEVICE;
+  if (d->stream_attrs_set) return B200_OK;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (d->stream_attrs_set) return B200_OK;
   const size_t maxsmem = 227 * 1024;
-  B200_TRY((stream_set_attr<B200_MODE_EXACT, false, 256>(maxsmem)));
-  B200_TRY((stream_set_attr<B200_MODE_EXACT, true, 256>(maxsmem)));
-  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, false, 256>(maxsmem)));
-  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, true, 256>(maxsmem)));
-  B200_TRY((stream_set_attr<B200_MODE_EXACT, false, 128>(maxsmem)));
-  B200_TRY((stream_set_attr<B200_MODE_EXACT, true, 128>(maxsmem)));
-  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, false, 128>(maxsmem)));
-  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, true, 128>(maxsmem)));
-  done = true;
+  B200_TRY((stream_set_attr<B200_MODE_EXACT, 256>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, 256>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT, 128>(maxsmem)));
+  B200_TRY((stream_set_attr<B200_MODE_EXACT_FMA, 128>(maxsmem)));
+  d->stream_attrs_set = true;
   return B200_OK;
 }
 
@@ -1115,7 +1189,6 @@ extern "C" int b200_init(int device)
   }
   if (device < 0 || device >= n) return set_error(B200_ERR_ARG, "device %d out of range [0,%d)", device, n);
   B200_CUDA_TRY(cudaSetDevice(device));
-  g_dev_ok = -1;
   return ensure_device();
 }
 
@@ -1291,15 +1364,17 @@ extern "C" int b200_csr_device_arrays(b200_csr_t A, const int32_t **d_ai, const 
 // dispatch
 // ---------------------------------------------------------------------------------------------
 // one place that instantiates the stream kernel for (threads per CTA, halo, index width)
-template <int MODE, int ADD, bool HALO>
+template <int MODE, int EPI, bool HALO>
 static int launch_stream_any(b200_csr_s *A, int grid, const int4 *tiles, int ntiles, const double *x,
                              const double *yin, double *y, const HaloArgs &h, cudaStream_t st,
-                             const double *aux = nullptr)
+                             const double *aux = nullptr, const DotArgs &dot = DotArgs{})
 {
   const Idx8Args ix{A->d_aj8, A->d_offs};
+  B200_TRY(stream_set_all_attrs(0, 0));   // first use on this device (a handle made on another one)
 #define B200_STREAM_GO(T, I8)                                                                       \
-  B200_LAUNCH((k_stream<MODE, ADD, T, HALO, I8>), grid, T + 32, A->stream_smem, st, tiles, ntiles, \
-              A->d_ai, A->d_aj, A->d_aa, x, yin, y, A->stream_cap, A->stream_stages, h, ix, aux)
+  B200_LAUNCH_PDL((k_stream<MODE, EPI, T, HALO, I8>), grid, T + 32, A->stream_smem, st, tiles, ntiles, \
+                  (const int *)A->d_ai, (const int *)A->d_aj, (const double *)A->d_aa, x, yin, y,     \
+                  (int)A->stream_cap, (int)A->stream_stages, h, ix, aux, dot)
   if (A->idx8) { if (A->stream_threads == 256) B200_STREAM_GO(256, true); else B200_STREAM_GO(128, true); }
   else { if (A->stream_threads == 256) B200_STREAM_GO(256, false); else B200_STREAM_GO(128, false); }
 #undef B200_STREAM_GO
@@ -1309,24 +1384,42 @@ static int launch_stream_any(b200_csr_s *A, int grid, const int4 *tiles, int nti
 template <int MODE, bool ADD>
 static int launch_stream(b200_csr_s *A, const double *x, const double *yin, double *y, cudaStream_t st)
 {
-  return launch_stream_any<MODE, ADD, false>(A, A->stream_grid, A->d_tiles, A->ntiles, x, yin, y, HaloArgs{}, st);
+  return launch_stream_any<MODE, ADD ? EPI_ADD : EPI_NONE, false>(A, A->stream_grid, A->d_tiles, A->ntiles, x, yin, y, HaloArgs{}, st);
 }
 
 // tiles [t0, t0 + nt) only: the row-blocked host pipeline
 template <int MODE, bool ADD>
 static int launch_stream_range(b200_csr_s *A, int t0, int nt, const double *x, const double *yin, double *y, cudaStream_t st)
 {
-  return launch_stream_any<MODE, ADD, false>(A, std::min(nt, A->stream_grid), A->d_tiles + t0, nt, x, yin, y, HaloArgs{}, st);
+  return launch_stream_any<MODE, ADD ? EPI_ADD : EPI_NONE, false>(A, std::min(nt, A->stream_grid), A->d_tiles + t0, nt, x, yin, y, HaloArgs{}, st);
 }
 
 // MatMult_MPIAIJ in one launch (see k_stream, HALO): push prologue on the first CTAs, then the
 // persistent stream loop, then the ghost rows.
 template <int MODE>
-static int launch_stream_halo_mode(b200_csr_s *A, const double *x, double *y, const HaloArgs &h, cudaStream_t st)
+static int launch_stream_halo_mode(b200_csr_s *A, const double *x, double *y, const HaloArgs &h, cudaStream_t st, const DotArgs *dot)
 {
   const int grid = A->stream_grid;  // cta_ptr / cta_rows were built for exactly this grid
   if (h.npush > grid) return set_error(B200_ERR_STATE, "more push blocks (%d) than CTAs (%d)", h.npush, grid);
-  return launch_stream_any<MODE, false, true>(A, grid, A->d_tiles, A->ntiles, x, nullptr, y, h, st);
+  if (dot) return launch_stream_any<MODE, EPI_DOT, true>(A, grid, A->d_tiles, A->ntiles, x, nullptr, y, h, st, nullptr, *dot);
+  return launch_stream_any<MODE, EPI_NONE, true>(A, grid, A->d_tiles, A->ntiles, x, nullptr, y, h, st);
+}
+
+// (x, y) over m rows into *out: the reduction of the plans that cannot fold it into the MatMult
+__global__ void __launch_bounds__(256) k_dot_simple(int m, const double *__restrict__ x, const double *__restrict__ y, double *out)
+{
+  __shared__ double sw[8];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < m; i += 256) t = __fma_rn(x[i], y[i], t);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sw[w];
+    *out = s;
+  }
 }
 
 namespace b200 {
@@ -1338,11 +1431,16 @@ int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid, int 
   *ntiles  = A->kernel_override && A->kernel_override != B200_KERNEL_STREAM ? 0 : A->ntiles;
   return B200_OK;
 }
-int launch_stream_halo(b200_csr_t A, const double *x, double *y, int mode, const HaloArgs &h, cudaStream_t st)
+int launch_stream_halo(b200_csr_t A, const double *x, double *y, int mode, const HaloArgs &h, cudaStream_t st, const DotArgs *dot)
 {
   if (!A->ntiles) return set_error(B200_ERR_STATE, "fused halo launch needs the stream plan");
-  if (mode == B200_MODE_EXACT) return launch_stream_halo_mode<B200_MODE_EXACT>(A, x, y, h, st);
-  return launch_stream_halo_mode<B200_MODE_EXACT_FMA>(A, x, y, h, st);
+  if (mode == B200_MODE_EXACT) return launch_stream_halo_mode<B200_MODE_EXACT>(A, x, y, h, st, dot);
+  return launch_stream_halo_mode<B200_MODE_EXACT_FMA>(A, x, y, h, st, dot);
+}
+int stream_grid_of(b200_csr_t A)
+{
+  const int k = A->kernel_override ? A->kernel_override : A->kernel_exact;
+  return (k == B200_KERNEL_STREAM && A->ntiles) ? A->stream_grid : 0;
 }
 }  // namespace b200
 
@@ -1612,6 +1710,25 @@ static int spmv_epilogue(b200_csr_s *A, int epi, const double *x, const double *
   else B200_LAUNCH((k_epilogue<3>), (A->m + 255) / 256, 256, 0, st, A->m, x, b, dinv, y);
   return B200_OK;
 }
+
+// w = A x with (x, w) folded into the stream kernel's epilogue (EPI_DOT); other plans run their
+// MatMult and then reduce in one CTA-sized pass (they serve small or skewed matrices).
+namespace b200 {
+int spmv_dot(b200_csr_t A, const double *x, double *y, int mode, const DotArgs &dot, cudaStream_t st)
+{
+  if (A->m == 0) { B200_CUDA_TRY(cudaMemsetAsync(dot.out, 0, sizeof(double), st)); return B200_OK; }
+  int kernel = A->kernel_override;
+  if (!kernel) kernel = (mode == B200_MODE_FAST) ? A->kernel_fast : A->kernel_exact;
+  if (kernel == B200_KERNEL_STREAM && dot.partials) {
+    const HaloArgs none{};
+    if (mode == B200_MODE_EXACT) return launch_stream_any<B200_MODE_EXACT, EPI_DOT, false>(A, A->stream_grid, A->d_tiles, A->ntiles, x, nullptr, y, none, st, nullptr, dot);
+    return launch_stream_any<B200_MODE_EXACT_FMA, EPI_DOT, false>(A, A->stream_grid, A->d_tiles, A->ntiles, x, nullptr, y, none, st, nullptr, dot);
+  }
+  B200_TRY(spmv_dispatch<false>(A, x, nullptr, y, mode, st));
+  B200_LAUNCH(k_dot_simple, 1, 256, 0, st, A->m, x, (const double *)y, dot.out);
+  return B200_OK;
+}
+}  // namespace b200
 
 extern "C" int b200_spmv_residual(b200_csr_t A, const double *d_x, const double *d_b, double *d_r, int mode, void *stream)
 {

@@ -313,3 +313,42 @@ extern "C" int b200_gen_powerlaw_fill(int32_t m, int32_t n, double alpha, int32_
   });
   return B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// BASELINE configs[3]: 27-point box stencil on an N^3 grid, non-periodic, natural
+// ordering, columns ascending; off-diagonal -1, diagonal = number of neighbours; nnz = (3N-2)^3.
+// seed != 0 replaces the values by uniform [-1,1) draws indexed by the non-zero position (identical
+// to tests/gen.py::stencil27).  ai[N^3 + 1]; aj / aa may be NULL for a sizing call.
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200_gen_stencil27(int32_t N, uint64_t seed, int32_t *ai, int32_t *aj, double *aa)
+{
+  if (N < 1 || !ai) return set_error(B200_ERR_ARG, "b200_gen_stencil27: bad argument");
+  const long long n = (long long)N * N * N;
+  if (n > 2147483647LL / 27) return set_error(B200_ERR_ARG, "27-point matrix exceeds int32 non-zeros");
+  auto span = [N](int c) { return (c > 0) + 1 + (c < N - 1); };
+  ai[0] = 0;
+  for (int k = 0; k < N; ++k)
+    for (int j = 0; j < N; ++j)
+      for (int i = 0; i < N; ++i) {
+        const long long r = ((long long)k * N + j) * N + i;
+        ai[r + 1] = ai[r] + span(i) * span(j) * span(k);
+      }
+  if (!aj || !aa) return B200_OK;
+  parallel_for((int)n, [&](int a, int b) {
+    for (int r = a; r < b; ++r) {
+      const int i = r % N, j = (r / N) % N, k = r / (N * N);
+      long long p = ai[r];
+      const int cnt = ai[r + 1] - ai[r];
+      for (int dk = -1; dk <= 1; ++dk)
+        for (int dj = -1; dj <= 1; ++dj)
+          for (int di = -1; di <= 1; ++di) {
+            if (i + di < 0 || i + di >= N || j + dj < 0 || j + dj >= N || k + dk < 0 || k + dk >= N) continue;
+            aj[p] = r + di + dj * N + dk * N * N;
+            if (seed) aa[p] = (double)(splitmix64(seed ^ (uint64_t)p) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+            else aa[p] = (di == 0 && dj == 0 && dk == 0) ? (double)(cnt - 1) : -1.0;
+            ++p;
+          }
+    }
+  });
+  return B200_OK;
+}

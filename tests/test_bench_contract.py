@@ -52,7 +52,7 @@ def test_reference_arm_does_not_map_the_product_library():
     """The reference arm must run on oracle/ alone: no libb200aij.so / libb200petsc.so in its address
     space (the driver records which in-tree .so files each arm loads)."""
     code = ("import sys, argparse; sys.path.insert(0, %r); import bench; "
-            "bench.run_reference(argparse.Namespace(grid=20, steps=1, warmup=1, gpus=1)); "
+            "bench.run_reference(argparse.Namespace(grid=20, steps=1, warmup=1, gpus=1, workload='matmult')); "
             "maps = open('/proc/self/maps').read(); "
             "assert 'libb200' not in maps, [l for l in maps.splitlines() if 'libb200' in l]; "
             "assert 'petsc_openacc_b200' not in sys.modules; "
