@@ -91,8 +91,17 @@ int b200_mpiaij_allreduce_sum(b200_mpiaij_t M, double *d_vals, int32_t nvals, vo
 /* KSPCG + PCJACOBI; d_b, d_x are this rank's rows; collective over the ranks                   */
 int b200_mpiaij_cg_jacobi(b200_mpiaij_t M, const double *d_b, double *d_x, double rtol, double atol,
                           int32_t max_it, int mode, b200_cg_result_t *res, void *stream);
-/* non-zero after a flag wait ran out of its spin budget (B200_MPIAIJ_TIMEOUT_MS, default 2000) */
+/* B200_ERR_TIMEOUT after a flag wait ran out of its spin budget (B200_MPIAIJ_TIMEOUT_MS, default
+ * 10000): the kernel gave up waiting for a peer and the y of that MatMult is not valid.  The
+ * asynchronous entries (b200_mpiaij_mult, _mult_finish, _mult_end) cannot return it themselves: call
+ * this after synchronising, before trusting y.  b200_mpiaij_mult_host and b200_mpiaij_cg_jacobi,
+ * which synchronise anyway, call it for you.  Reporting clears the condition.                     */
 int b200_mpiaij_check(b200_mpiaij_t M);
+/* The push exchange alternates two receive buffers and relies on every rank this one sends to also
+ * being one it receives from (true for structurally symmetric matrices).  B200_OK, or
+ * B200_ERR_STATE with the first unmatched peer; b200_mpiaij_mult* refuse such a pattern with the
+ * same error.  Host only, valid after every b200_mpiaij_set_peer_garray call.                     */
+int b200_mpiaij_pattern_symmetric(b200_mpiaij_t M, int32_t *first_unmatched_peer);
 
 #ifdef __cplusplus
 }

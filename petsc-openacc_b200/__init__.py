@@ -322,6 +322,7 @@ MPIAIJ_SYMBOLS = [
     "b200_mpiaij_mult_end", "b200_mpiaij_mult", "b200_mpiaij_pack", "b200_mpiaij_mult_add_ghost",
     "b200_mpiaij_check", "b200_mpiaij_mult_host", "b200_mpiaij_mult_finish",
     "b200_mpiaij_set_rank_window", "b200_mpiaij_allreduce_sum", "b200_mpiaij_cg_jacobi",
+    "b200_mpiaij_pattern_symmetric",
 ]
 ABI_SYMBOLS += MPIAIJ_SYMBOLS
 
@@ -435,6 +436,12 @@ class MpiAij:
 
     def check(self):
         check(lib.b200_mpiaij_check(self._h))
+
+    def pattern_symmetric(self):
+        """(True, -1) or (False, first peer this rank sends to but does not receive from)."""
+        peer = C.c_int32(-1)
+        rc = lib.b200_mpiaij_pattern_symmetric(self._h, C.byref(peer))
+        return rc == 0, peer.value
 
 
 def gen_poisson7(M, size=1, rank=0, refpoint=True, vectors=False):

@@ -152,8 +152,9 @@ struct b200_mpiaij_s {
   unsigned long long seq = 0;
   cudaStream_t side = nullptr, hstream = nullptr;
   double *d_hx = nullptr, *d_hy = nullptr;
+  unsigned long long *h_err = nullptr;   // pinned copy of the time-out word (host-vector entry)
   cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
-  unsigned long long timeout_ns = 2000ull * 1000000ull;
+  unsigned long long timeout_ns = 10000ull * 1000000ull;
   int *d_cta_ptr = nullptr, *d_cta_rows = nullptr;  // fused launch: B rows grouped by owning CTA
   // all-reduce: every rank's window (own included), in rank order
   std::vector<unsigned char *> all_windows;
@@ -234,6 +235,7 @@ extern "C" int b200_mpiaij_destroy(b200_mpiaij_t M)
   if (M->side) cudaStreamDestroy(M->side);
   if (M->hstream) cudaStreamDestroy(M->hstream);
   cudaFree(M->d_hx); cudaFree(M->d_hy);
+  if (M->h_err) cudaFreeHost(M->h_err);
   if (M->ev_fork) cudaEventDestroy(M->ev_fork);
   if (M->ev_join) cudaEventDestroy(M->ev_join);
   delete M;
@@ -330,7 +332,7 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
   B200_CUDA_TRY(cudaStreamCreateWithFlags(&M->side, cudaStreamNonBlocking));
   B200_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_fork, cudaEventDisableTiming));
   B200_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_join, cudaEventDisableTiming));
-  M->timeout_ns = (unsigned long long)env_int("B200_MPIAIJ_TIMEOUT_MS", 2000) * 1000000ull;
+  M->timeout_ns = (unsigned long long)env_int("B200_MPIAIJ_TIMEOUT_MS", 10000) * 1000000ull;
   // fused launch: group B's compressed rows by the stream CTA that owns the tile of the row
   // (tile t belongs to CTA t % grid), so that each CTA finishes exactly the rows it wrote
   {
@@ -409,10 +411,32 @@ extern "C" int b200_mpiaij_open_peer_window(b200_mpiaij_t M, int32_t peer, const
   return B200_OK;
 }
 
+// The two lvec buffers alternate with the MatMult number and nothing tells a sender that a buffer has
+// been read: what keeps a sender from running two MatMults ahead of a receiver is that it waits for
+// that receiver's flag itself, every MatMult.  That holds exactly when every rank this one sends to
+// is also one it receives from (always true for a structurally symmetric matrix such as the
+// reference's).  Other patterns are refused here; the caller-owned transport (b200_mpiaij_pack +
+// b200_mpiaij_mult_add_ghost, e.g. over NCCL) has no such restriction.
+extern "C" int b200_mpiaij_pattern_symmetric(b200_mpiaij_t M, int32_t *first_unmatched_peer)
+{
+  if (!M) return set_error(B200_ERR_ARG, "null handle");
+  if (first_unmatched_peer) *first_unmatched_peer = -1;
+  for (auto &s : M->sends)
+    if (!std::binary_search(M->srcs.begin(), M->srcs.end(), s.peer)) {
+      if (first_unmatched_peer) *first_unmatched_peer = s.peer;
+      return set_error(B200_ERR_STATE,
+                       "rank %d sends ghost values to rank %d but receives none from it: the push exchange needs a "
+                       "symmetric communication pattern (use b200_mpiaij_pack / b200_mpiaij_mult_add_ghost with your own transport)",
+                       M->rank, s.peer);
+    }
+  return B200_OK;
+}
+
 // freeze the send side: flat index array, CTA table, per-peer destinations
 static int prepare_push(b200_mpiaij_s *M)
 {
   if (M->push_ready) return B200_OK;
+  B200_TRY(b200_mpiaij_pattern_symmetric(M, nullptr));
   cudaFree(M->d_send_idx); cudaFree(M->d_blocks); cudaFree(M->d_peers); cudaFree(M->d_done);
   M->d_send_idx = nullptr; M->d_blocks = nullptr; M->d_peers = nullptr; M->d_done = nullptr;
   std::vector<int32_t>   flat;
@@ -562,11 +586,16 @@ extern "C" int b200_mpiaij_mult_host(b200_mpiaij_t M, const double *h_x, double 
     B200_CUDA_TRY(cudaMalloc((void **)&M->d_hx, std::max<size_t>(M->nloc, 1) * sizeof(double)));
     B200_CUDA_TRY(cudaMalloc((void **)&M->d_hy, std::max<size_t>(M->nloc, 1) * sizeof(double)));
     B200_CUDA_TRY(cudaStreamCreateWithFlags(&M->hstream, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaHostAlloc((void **)&M->h_err, sizeof(unsigned long long), cudaHostAllocDefault));
+    *M->h_err = 0;
   }
   B200_CUDA_TRY(cudaMemcpyAsync(M->d_hx, h_x, (size_t)M->nloc * sizeof(double), cudaMemcpyHostToDevice, M->hstream));
   B200_TRY(b200_mpiaij_mult(M, M->d_hx, M->d_hy, mode, M->hstream));
   B200_CUDA_TRY(cudaMemcpyAsync(h_y, M->d_hy, (size_t)M->nloc * sizeof(double), cudaMemcpyDeviceToHost, M->hstream));
+  // the time-out word rides down behind y: this entry synchronises anyway, so it can report it
+  B200_CUDA_TRY(cudaMemcpyAsync(M->h_err, (unsigned long long *)M->d_window + ERR_WORD, sizeof(unsigned long long), cudaMemcpyDeviceToHost, M->hstream));
   B200_CUDA_TRY(cudaStreamSynchronize(M->hstream));
+  if (*M->h_err) return b200_mpiaij_check(M);
   return B200_OK;
 }
 
@@ -600,7 +629,12 @@ extern "C" int b200_mpiaij_check(b200_mpiaij_t M)
   if (!M || !M->uploaded) return B200_OK;
   unsigned long long e = 0;
   B200_CUDA_TRY(cudaMemcpy(&e, (unsigned long long *)M->d_window + ERR_WORD, sizeof e, cudaMemcpyDeviceToHost));
-  if (e) return set_error(B200_ERR_TIMEOUT, "rank %d: a halo flag was not seen within the spin budget", M->rank);
+  if (e) {
+    // report once: the word is cleared so that a later, healthy MatMult is not blamed for this one
+    B200_CUDA_TRY(cudaMemset((unsigned long long *)M->d_window + ERR_WORD, 0, sizeof e));
+    return set_error(B200_ERR_TIMEOUT, "rank %d: a halo flag was not seen within %llu ms (B200_MPIAIJ_TIMEOUT_MS); the result of that MatMult is not valid",
+                     M->rank, M->timeout_ns / 1000000ull);
+  }
   return B200_OK;
 }
 

@@ -135,3 +135,22 @@ def test_distributed_cg_two_gpus(pk, cuda):
     assert r["allreduce_ok"] and r["reason"] > 0
     assert len(set(r["its_all"])) == 1 and r["its"] == its, (r, its)
     assert r["linf_err"] < 0.02
+
+
+def test_halo_stress_two_gpus(cuda):
+    """Thousands of unsynchronised MatMults with a different x each, skewed ranks, every result
+    checked (tests/mpiaij_stress_worker.py); the 8-GPU run of the same worker is logged under profiles/."""
+    import json
+    import os
+    import subprocess
+    import sys
+    torch = cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + os.getpid() % 200), os.path.join(root, "tests", "mpiaij_stress_worker.py"), "40", "3000"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert r["first_result_equals_oracle"] and r["mismatches"] == 0, r

@@ -110,3 +110,34 @@ def test_two_rank_gloo_exchange_of_scatter_lists(pk):
         proff = oracle.scatter_recv_offsets(base, refs[peer]["garray"])
         assert np.array_equal(idx, refs[peer]["garray"][proff[r]:proff[r + 1]] - base[r])
         assert off == proff[r] and len(idx) == N * N
+
+
+def test_unsymmetric_communication_pattern_is_reported(pk):
+    """The push exchange alternates two receive buffers and needs every destination to be a source
+    too.  An upper-triangular coupling (rank 0 reads rank 1's rows, rank 1 reads nothing of rank 0's)
+    is reported by b200_mpiaij_pattern_symmetric -- and refused by the MatMult entries -- while the
+    reference problem at every rank count is symmetric."""
+    base = np.array([0, 3, 6], np.int32)
+    # rank 0: rows 0..2 with a column owned by rank 1; rank 1: rows 3..5, own columns only
+    r0 = pk.MpiAij(2, 0, base, [0, 2, 3, 5], [0, 4, 1, 2, 5], [1.0, 2.0, 3.0, 4.0, 5.0])
+    r1 = pk.MpiAij(2, 1, base, [0, 1, 2, 3], [3, 4, 5], [1.0, 1.0, 1.0])
+    g0, g1 = r0.garray(), r1.garray()
+    assert list(g0) == [4, 5] and len(g1) == 0
+    r0.set_peer_garray(1, g1)
+    r1.set_peer_garray(0, g0)
+    assert r0.pattern_symmetric() == (True, -1)          # rank 0 only receives
+    ok, peer = r1.pattern_symmetric()                    # rank 1 sends to 0 and receives nothing from it
+    assert not ok and peer == 0
+    assert "symmetric communication pattern" in pk.lib.b200_last_error().decode()
+    r0.destroy(); r1.destroy()
+    for size in (2, 4, 8):
+        ms = []
+        for rank in range(size):
+            p = oracle.poisson7(8, size=size, rank=rank)
+            ms.append(pk.MpiAij(size, rank, oracle.dmda_bases(8, 8, 8, size), p["ai"], p["aj"], p["aa"]))
+        for a in ms:
+            for b in ms:
+                if a is not b:
+                    a.set_peer_garray(b.rank, b.garray())
+        assert all(m.pattern_symmetric()[0] for m in ms)
+        [m.destroy() for m in ms]
