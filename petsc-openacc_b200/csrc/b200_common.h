@@ -107,6 +107,11 @@ struct HaloArgs {
   const int       *send_idx;
   unsigned        *done;
   int              npush;
+  // tile schedule of this launch: the CTA-major copy of the tile table and, per CTA, its [first, last)
+  // range in it (tiles dealt out by cost, ghost rows included, so that the CTAs that close many
+  // ghost rows stream fewer tiles); nullptr = tile t belongs to CTA t % grid
+  const int4      *sched_tiles;
+  const int       *sched_first;
   // receive side (VecScatterEnd + MatMultAdd of the off-diagonal block, compressed row)
   const int       *cta_ptr;    // per stream CTA: [first, last) in cta_rows
   const int       *cta_rows;   // compressed-row positions of B grouped by the CTA that owns the row's tile
@@ -154,6 +159,11 @@ int stream_plan_tiles(b200_csr_t A, int4 **d_tiles, int *ntiles, int *grid, int 
 int launch_stream_halo(b200_csr_t A, const double *x, double *y, int mode, const HaloArgs &h,
                        cudaStream_t st, const DotArgs *dot = nullptr);
 int stream_grid_of(b200_csr_t A);   // CTAs of the stream launch (0: the plan is not the stream kernel)
+// the row blocks of the host-vector pipeline (tile aligned, ~B200_HOST_BLOCK_ROWS rows): block b covers
+// rows [row0, row1) and reads x up to the end of block `need`; launch = A x for those rows only
+int host_block_count(b200_csr_t A, int mode);
+int host_block_info(b200_csr_t A, int b, int *row0, int *row1, int *need);
+int launch_host_block(b200_csr_t A, int b, const double *x, double *y, int mode, cudaStream_t st);
 // w = A x with (x, w) folded in when the plan is the stream kernel, else MatMult + a reduction
 int spmv_dot(b200_csr_t A, const double *x, double *y, int mode, const DotArgs &dot, cudaStream_t st);
 

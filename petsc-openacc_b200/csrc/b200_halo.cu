@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <queue>
 #include <vector>
 
 #include "../../include/b200_mpiaij.h"
@@ -153,9 +154,16 @@ struct b200_mpiaij_s {
   cudaStream_t side = nullptr, hstream = nullptr;
   double *d_hx = nullptr, *d_hy = nullptr;
   unsigned long long *h_err = nullptr;   // pinned copy of the time-out word (host-vector entry)
+  // row-blocked pipeline of the host-vector entry
+  cudaStream_t hs_up = nullptr, hs_dn = nullptr, hs_push = nullptr;
+  cudaEvent_t  ev_push = nullptr;
+  std::vector<cudaEvent_t> evx, evk;
+  double *d_gbuf = nullptr, *h_gbuf = nullptr;
   cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
   unsigned long long timeout_ns = 10000ull * 1000000ull;
   int *d_cta_ptr = nullptr, *d_cta_rows = nullptr;  // fused launch: B rows grouped by owning CTA
+  int4 *d_sched_tiles = nullptr;                    // fused launch: the tile table in CTA-major order
+  int  *d_sched_first = nullptr;                    //               and each CTA's range in it
   // all-reduce: every rank's window (own included), in rank order
   std::vector<unsigned char *> all_windows;
   std::vector<char> all_windows_opened;
@@ -227,7 +235,7 @@ extern "C" int b200_mpiaij_destroy(b200_mpiaij_t M)
   if (M->A) b200_csr_destroy(M->A);
   if (M->B) b200_csr_destroy(M->B);
   cudaFree(M->d_cpi); cudaFree(M->d_ridx); cudaFree(M->d_bj); cudaFree(M->d_ba); cudaFree(M->d_srcs);
-  cudaFree(M->d_cta_ptr); cudaFree(M->d_cta_rows);
+  cudaFree(M->d_cta_ptr); cudaFree(M->d_cta_rows); cudaFree(M->d_sched_tiles); cudaFree(M->d_sched_first);
   cudaFree(M->d_all_windows);
   for (int q = 0; q < (int)M->all_windows.size(); ++q)
     if (q != M->rank && M->all_windows[q] && M->all_windows_opened[q]) cudaIpcCloseMemHandle(M->all_windows[q]);
@@ -236,6 +244,11 @@ extern "C" int b200_mpiaij_destroy(b200_mpiaij_t M)
   if (M->hstream) cudaStreamDestroy(M->hstream);
   cudaFree(M->d_hx); cudaFree(M->d_hy);
   if (M->h_err) cudaFreeHost(M->h_err);
+  if (M->hs_up) { cudaStreamDestroy(M->hs_up); cudaStreamDestroy(M->hs_dn); cudaStreamDestroy(M->hs_push); cudaEventDestroy(M->ev_push); }
+  for (auto &e : M->evx) cudaEventDestroy(e);
+  for (auto &e : M->evk) cudaEventDestroy(e);
+  cudaFree(M->d_gbuf);
+  if (M->h_gbuf) cudaFreeHost(M->h_gbuf);
   if (M->ev_fork) cudaEventDestroy(M->ev_fork);
   if (M->ev_join) cudaEventDestroy(M->ev_join);
   delete M;
@@ -342,18 +355,67 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
     if (ntiles && grid > 0 && env_int("B200_MPIAIJ_FUSED", 1)) {
       std::vector<int4> tiles((size_t)ntiles);
       B200_CUDA_TRY(cudaMemcpy(tiles.data(), d_tiles, sizeof(int4) * (size_t)ntiles, cudaMemcpyDeviceToHost));
+      // ghost rows per tile
+      std::vector<int> tile_of(M->ridx.size()), gcount((size_t)ntiles, 0);
+      {
+        int t = 0;
+        for (size_t c = 0; c < M->ridx.size(); ++c) {
+          while (t < ntiles && M->ridx[c] >= tiles[t].y) ++t;
+          tile_of[c] = t;
+          gcount[t]++;
+        }
+      }
+      // Tile -> CTA.  Round-robin keeps all CTAs sweeping the matrix in lockstep (the x window they
+      // gather from stays in L2), but a face of the sub-box that is contiguous in memory puts 256 ghost
+      // rows into every one of ~90 consecutive tiles, and a CTA that owns one of them would close
+      // those rows on top of a full share of tiles and finish last.  So: the ghost-heavy tiles are
+      // dealt out first, each charged 1 + ghost rows / 128 tile times (256 ghost rows ~ two tiles,
+      // measured with scripts/probe_fused2.py); then the other tiles go, IN INDEX ORDER, to the CTA with
+      // the least load so far -- round-robin again, except that a CTA holding a heavy tile sits out
+      // as many rounds as it was charged.  Each CTA's tiles stay in ascending order.
+      // B200_MPIAIJ_SCHED=0 keeps tile t on CTA t % grid.
+      std::vector<int> cta_of((size_t)ntiles);
+      const bool lpt = env_int("B200_MPIAIJ_SCHED", 1) != 0;
+      if (lpt) {
+        using Load = std::pair<double, int>;
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+        for (int b = 0; b < grid; ++b) heap.push({0.0, b});
+        auto deal = [&](int t) {
+          Load top = heap.top();
+          heap.pop();
+          cta_of[t] = top.second;
+          heap.push({top.first + 1.0 + gcount[t] / 128.0, top.second});
+        };
+        for (int t = 0; t < ntiles; ++t) if (gcount[t] >= 64) deal(t);
+        for (int t = 0; t < ntiles; ++t) if (gcount[t] < 64) deal(t);
+      } else {
+        for (int t = 0; t < ntiles; ++t) cta_of[t] = t % grid;
+      }
+      std::vector<int>  first((size_t)grid + 1, 0);
+      std::vector<int4> sched_tiles((size_t)ntiles);
+      for (int t = 0; t < ntiles; ++t) first[cta_of[t] + 1]++;
+      for (int b = 0; b < grid; ++b) first[b + 1] += first[b];
+      {
+        std::vector<int> next(first.begin(), first.end() - 1);
+        for (int t = 0; t < ntiles; ++t) sched_tiles[next[cta_of[t]]++] = tiles[t];   // ascending inside a CTA
+      }
+      for (int b = 0; b < grid; ++b)
+        if (first[b + 1] == first[b]) return set_error(B200_ERR_STATE, "tile schedule left CTA %d without work", b);
       std::vector<int> owner(M->ridx.size()), ptr((size_t)grid + 1, 0), rows(M->ridx.size());
-      int t = 0;
       for (size_t c = 0; c < M->ridx.size(); ++c) {
-        while (t < ntiles && M->ridx[c] >= tiles[t].y) ++t;
-        owner[c] = t % grid;
+        owner[c] = cta_of[tile_of[c]];
         ptr[owner[c] + 1]++;
       }
       for (int b = 0; b < grid; ++b) ptr[b + 1] += ptr[b];
       std::vector<int> next(ptr.begin(), ptr.end() - 1);
       for (size_t c = 0; c < M->ridx.size(); ++c) rows[next[owner[c]]++] = (int)c;
+      if (env_int("B200_MPIAIJ_PROBE_NOGHOST", 0)) std::fill(ptr.begin(), ptr.end(), 0);   // timing probe only: wrong results
       B200_TRY(up(&M->d_cta_ptr, ptr));
       B200_TRY(up(&M->d_cta_rows, rows));
+      if (lpt) {
+        B200_TRY(up(&M->d_sched_tiles, sched_tiles));
+        B200_TRY(up(&M->d_sched_first, first));
+      }
       M->fused_grid = grid;
       M->fused_ok = true;
     }
@@ -526,6 +588,7 @@ static HaloArgs fused_args(b200_mpiaij_s *M, bool with_push)
   HaloArgs h{};
   h.blocks = M->d_blocks; h.peers = M->d_peers; h.send_idx = M->d_send_idx; h.done = M->d_done;
   h.npush = with_push ? M->npush_blocks : 0;
+  h.sched_tiles = M->d_sched_tiles; h.sched_first = M->d_sched_first;
   h.cta_ptr = M->d_cta_ptr; h.cta_rows = M->d_cta_rows; h.cpi = M->d_cpi; h.ridx = M->d_ridx; h.bj = M->d_bj; h.ba = M->d_ba;
   h.lvec = (const double *)(M->d_window + WINDOW_HDR_BYTES) + (size_t)(M->seq & 1) * M->ngpad;
   h.flags = (const unsigned long long *)M->d_window; h.srcs = M->d_srcs; h.nsrc = (int)M->srcs.size();
@@ -578,6 +641,71 @@ extern "C" int b200_mpiaij_mult(b200_mpiaij_t M, const double *d_x, double *d_y,
   return mpiaij_mult(M, d_x, d_y, mode, stream, nullptr);
 }
 
+// y rows that touch a ghost, packed: the tail of the pipelined host-vector MatMult
+__global__ void k_gather_rows(int n, const int *__restrict__ ridx, const double *__restrict__ y, double *__restrict__ out)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = y[ridx[t]];
+}
+
+// Row-blocked pipeline of the host-vector MatMult_MPIAIJ (the reference's step 4,
+// src/openacc-step4/MatMult_SeqAIJ.patch:51-72, on the row-partitioned matrix): x goes up in blocks;
+// block b's A x starts as soon as the last block it reads has landed and its y rows go down while
+// later blocks are still on their way up (PCIe is full duplex); the halo push follows the last
+// upload; the ghost rows (~2 % of the rows, scattered over every block) are finished last, packed,
+// brought down in one small copy and patched into h_y by the host.  Same arithmetic, same order.
+static int mult_host_pipelined(b200_mpiaij_s *M, const double *h_x, double *h_y, int mode, int nblk)
+{
+  if (!M->hs_up) {
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&M->hs_up, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&M->hs_dn, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&M->hs_push, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaEventCreateWithFlags(&M->ev_push, cudaEventDisableTiming));
+    const size_t ng = std::max<size_t>(M->ridx.size(), 1);
+    B200_CUDA_TRY(cudaMalloc((void **)&M->d_gbuf, ng * sizeof(double)));
+    B200_CUDA_TRY(cudaHostAlloc((void **)&M->h_gbuf, ng * sizeof(double), cudaHostAllocDefault));
+  }
+  while ((int)M->evx.size() < nblk) {
+    cudaEvent_t a, b;
+    B200_CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    B200_CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    M->evx.push_back(a); M->evk.push_back(b);
+  }
+  cudaStream_t sk = M->hstream;
+  int r0, r1, need;
+  for (int b = 0; b < nblk; ++b) {
+    host_block_info(M->A, b, &r0, &r1, &need);
+    B200_CUDA_TRY(cudaMemcpyAsync(M->d_hx + r0, h_x + r0, (size_t)(r1 - r0) * sizeof(double), cudaMemcpyHostToDevice, M->hs_up));
+    B200_CUDA_TRY(cudaEventRecord(M->evx[b], M->hs_up));
+  }
+  // VecScatterBegin once every row of x is on the device (the boundary values lie all over it)
+  B200_CUDA_TRY(cudaStreamWaitEvent(M->hs_push, M->evx[nblk - 1], 0));
+  B200_TRY(b200_mpiaij_mult_begin(M, M->d_hx, M->hs_push));
+  B200_CUDA_TRY(cudaEventRecord(M->ev_push, M->hs_push));
+  for (int b = 0; b < nblk; ++b) {
+    host_block_info(M->A, b, &r0, &r1, &need);
+    B200_CUDA_TRY(cudaStreamWaitEvent(sk, M->evx[need], 0));
+    B200_TRY(launch_host_block(M->A, b, M->d_hx, M->d_hy, mode, sk));
+    B200_CUDA_TRY(cudaEventRecord(M->evk[b], sk));
+    B200_CUDA_TRY(cudaStreamWaitEvent(M->hs_dn, M->evk[b], 0));
+    B200_CUDA_TRY(cudaMemcpyAsync(h_y + r0, M->d_hy + r0, (size_t)(r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, M->hs_dn));
+  }
+  // VecScatterEnd + MatMultAdd on the ghost rows, then their final values in one packed copy
+  B200_CUDA_TRY(cudaStreamWaitEvent(sk, M->ev_push, 0));
+  B200_TRY(b200_mpiaij_mult_end(M, M->d_hy, mode, sk));
+  const int ng = (int)M->ridx.size();
+  if (ng) {
+    B200_LAUNCH(k_gather_rows, (ng + 255) / 256, 256, 0, sk, ng, (const int *)M->d_ridx, (const double *)M->d_hy, M->d_gbuf);
+    B200_CUDA_TRY(cudaMemcpyAsync(M->h_gbuf, M->d_gbuf, (size_t)ng * sizeof(double), cudaMemcpyDeviceToHost, sk));
+  }
+  B200_CUDA_TRY(cudaMemcpyAsync(M->h_err, (unsigned long long *)M->d_window + ERR_WORD, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sk));
+  B200_CUDA_TRY(cudaStreamSynchronize(M->hs_dn));
+  B200_CUDA_TRY(cudaStreamSynchronize(sk));
+  for (int c = 0; c < ng; ++c) h_y[M->ridx[c]] = M->h_gbuf[c];
+  if (*M->h_err) return b200_mpiaij_check(M);
+  return B200_OK;
+}
+
 // MatMult_MPIAIJ(Mat,Vec,Vec) with host Vecs: upload this rank's x rows, multiply, download y.
 extern "C" int b200_mpiaij_mult_host(b200_mpiaij_t M, const double *h_x, double *h_y, int mode)
 {
@@ -589,6 +717,9 @@ extern "C" int b200_mpiaij_mult_host(b200_mpiaij_t M, const double *h_x, double 
     B200_CUDA_TRY(cudaHostAlloc((void **)&M->h_err, sizeof(unsigned long long), cudaHostAllocDefault));
     *M->h_err = 0;
   }
+  B200_TRY(prepare_push(M));
+  const int nblk = env_int("B200_MPIAIJ_HOST_PIPELINE", 1) ? host_block_count(M->A, mode) : 0;
+  if (nblk >= 2) return mult_host_pipelined(M, h_x, h_y, mode, nblk);
   B200_CUDA_TRY(cudaMemcpyAsync(M->d_hx, h_x, (size_t)M->nloc * sizeof(double), cudaMemcpyHostToDevice, M->hstream));
   B200_TRY(b200_mpiaij_mult(M, M->d_hx, M->d_hy, mode, M->hstream));
   B200_CUDA_TRY(cudaMemcpyAsync(h_y, M->d_hy, (size_t)M->nloc * sizeof(double), cudaMemcpyDeviceToHost, M->hstream));

@@ -231,7 +231,7 @@ enum { EPI_NONE = 0, EPI_ADD = 1, EPI_RESIDUAL = 2, EPI_JACOBI = 3, EPI_DOT = 4 
 
 template <int MODE, int EPI, int THREADS, bool HALO, bool IDX8>
 __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
-    k_stream(const int4 *__restrict__ tiles, int ntiles, const int *__restrict__ ii,
+    k_stream(const int4 *__restrict__ tiles_in, int ntiles, const int *__restrict__ ii,
              const int *__restrict__ aj, const double *__restrict__ aa,
              const double *__restrict__ x, const double *yin, double *y, int cap, int stages,
              const HaloArgs h, const Idx8Args ix, const double *__restrict__ aux, const DotArgs dot)
@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
   pdl_launch_dependents();
   const int bid = (int)blockIdx.x;
   const int nb  = (int)gridDim.x;
+  const int4 *__restrict__ tiles = tiles_in;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full  = reinterpret_cast<uint64_t *>(smem);
   uint64_t *empty = full + stages;
@@ -264,6 +265,12 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
   const size_t   aabytes = (size_t)(cap + STREAM_PAD) * 8, ajbytes = stream_aj_bytes(cap, IDX8);
 
   const int tid = threadIdx.x;
+  // this CTA's tiles: every grid-th one, or its range of the launch's own schedule (HALO)
+  const bool sched = HALO && h.sched_first != nullptr;
+  if (sched) tiles = h.sched_tiles;
+  const int tile0 = sched ? __ldg(h.sched_first + bid) : bid;
+  const int tile1 = sched ? __ldg(h.sched_first + bid + 1) : ntiles;
+  const int tstep = sched ? 1 : nb;
   if (IDX8) {
     // all 256 table entries, also when the CTA has fewer than 256 threads (THREADS = 128 -> 160)
     for (int t = tid; t < 256; t += THREADS + 32) soffs[t] = __ldg(ix.offs + t);
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     if (tid == THREADS) {
       const uint64_t pol = l2_policy_evict_first();
       int it = 0;
-      for (int tile = bid; tile < ntiles; tile += nb, ++it) {
+      for (int tile = tile0; tile < tile1; tile += tstep, ++it) {
         const int s = it % stages;
         if (it >= stages) mbar_wait(&empty[s], ((it / stages) - 1) & 1);
         const int4 d   = __ldg(tiles + tile);
@@ -313,6 +320,19 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
         }
         bulk_g2s(sii, ii + r0a, (uint32_t)nr * 4, &full[s], pol);
       }
+    } else if (HALO) {
+      // The other 31 lanes of the producer warp have nothing to do: they walk this CTA's ghost-row
+      // list once and pull what the closing phase will read (row list, B's row pointers, row numbers,
+      // column positions, values -- all constant) into L2, so that the dependent loads at the very end
+      // of the CTA, which sit on the critical path of the launch, are L2 hits instead of DRAM round trips.
+      const int q0 = __ldg(h.cta_ptr + bid), q1 = __ldg(h.cta_ptr + bid + 1);
+      for (int q = q0 + (tid - THREADS - 1); q < q1; q += 31) {
+        const int c  = __ldg(h.cta_rows + q);
+        const int lo = __ldg(h.cpi + c);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(h.ridx + c));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(h.bj + lo));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(h.ba + lo));
+      }
     }
     return;
   }
@@ -322,7 +342,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
   if (HALO && bid < h.npush) halo_push_block<THREADS>(h, x, bid);
   double dacc = 0.0;
   int it = 0;
-  for (int tile = bid; tile < ntiles; tile += nb, ++it) {
+  for (int tile = tile0; tile < tile1; tile += tstep, ++it) {
     const int  s = it % stages;
     const int4 d = __ldg(tiles + tile);
     unsigned char *st  = stage0 + (size_t)s * sbytes;
@@ -599,6 +619,95 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_wmerge: the exact summation order on skewed matrices, warp granular.  The matrix is cut into
+// CHUNKS of at most WM_CAP consecutive non-zeros: either a run of whole rows (each at most WM_CAP
+// long) or one piece of a longer row.  A warp stages a chunk -- column indices and values coalesced
+// over the non-zeros, four per lane, all gathers of x in flight together -- as rounded products (or
+// a and x side by side for the fused chain) in its own slice of shared memory, then its lanes sum
+// the chunk's rows left to right, one row per lane; a long row is summed by lane 0 chunk after
+// chunk with the partial sum carried in a register.  No block barrier, no tile is ever cut short by
+// a long row next to it (what left the block-granular k_mergex tiles a quarter full on the power-law
+// matrix), and persistent warps draw BLOCKS of consecutive chunks from an atomic counter, so a
+// 10,000-entry row delays one warp, not a CTA.
+// chunks[c] = {first row, rows (>= 0) | -1 middle / -2 first / -3 last piece of a long row, k0, k1}.
+// ---------------------------------------------------------------------------------------------
+#define WM_CAP 128
+#define WM_WARPS 8
+#define WM_PER (WM_CAP / 32)
+template <int MODE, bool ADD>
+__global__ void __launch_bounds__(WM_WARPS * 32)
+    k_wmerge(const int4 *__restrict__ chunks, const int *__restrict__ blk, int nblk, unsigned *counters,
+             const int *__restrict__ ii, const int *__restrict__ aj, const double *__restrict__ aa,
+             const double *__restrict__ x, const double *yin, double *y)
+{
+  constexpr bool PROD = (MODE == B200_MODE_EXACT);
+  __shared__ double sp[WM_WARPS][WM_CAP];
+  __shared__ double sx[WM_WARPS][PROD ? 1 : WM_CAP];
+  __shared__ int    srp[WM_WARPS][WM_CAP + 1];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  double carry = 0.0;   // lane 0: the running sum of a long row
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = (int)atomicAdd(counters, 1u);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= nblk) break;
+    const int c0 = __ldg(blk + b), c1 = __ldg(blk + b + 1);
+    for (int c = c0; c < c1; ++c) {
+      const int4 d = __ldg(chunks + c);
+      const int  n = d.w - d.z;
+      int    cj[WM_PER];
+      double av[WM_PER], xv[WM_PER];
+#pragma unroll
+      for (int j = 0; j < WM_PER; ++j) {
+        const int k = lane + 32 * j;
+        cj[j] = (k < n) ? ldg_s32_stream_policy(aj + d.z + k, pol_stream) : 0;
+        av[j] = (k < n) ? ldg_f64_stream_policy(aa + d.z + k, pol_stream) : 0.0;
+      }
+      if (d.y >= 0)
+        for (int j = lane; j <= d.y; j += 32) srp[w][j] = __ldg(ii + d.x + j) - d.z;
+#pragma unroll
+      for (int j = 0; j < WM_PER; ++j) xv[j] = (lane + 32 * j < n) ? ldg_f64_policy(x + cj[j], pol_keep) : 0.0;
+#pragma unroll
+      for (int j = 0; j < WM_PER; ++j) {
+        const int k = lane + 32 * j;
+        if (k < n) {
+          if (PROD) sp[w][k] = __dmul_rn(av[j], xv[j]);
+          else { sp[w][k] = av[j]; sx[w][k] = xv[j]; }
+        }
+      }
+      __syncwarp();
+      if (d.y >= 0) {
+        for (int r = lane; r < d.y; r += 32) {
+          const int row = d.x + r;
+          double    sum = ADD ? yin[row] : 0.0;
+          const int lo = srp[w][r], hi = srp[w][r + 1];
+          if (PROD) for (int k = lo; k < hi; ++k) sum = __dadd_rn(sum, sp[w][k]);
+          else for (int k = lo; k < hi; ++k) sum = __fma_rn(sp[w][k], sx[w][k], sum);
+          y[row] = sum;
+        }
+      } else if (lane == 0) {
+        if (d.y == -2) carry = ADD ? yin[d.x] : 0.0;
+        if (n == WM_CAP) {
+#pragma unroll 16
+          for (int l = 0; l < WM_CAP; ++l) carry = PROD ? __dadd_rn(carry, sp[w][l]) : __fma_rn(sp[w][l], sx[w][l], carry);
+        } else {
+          for (int l = 0; l < n; ++l) carry = PROD ? __dadd_rn(carry, sp[w][l]) : __fma_rn(sp[w][l], sx[w][l], carry);
+        }
+        if (d.y == -3) y[d.x] = carry;
+      }
+      __syncwarp();
+    }
+  }
+  // the last warp out re-arms the work counter for the next launch
+  if (lane == 0) {
+    __threadfence();
+    const unsigned total = gridDim.x * WM_WARPS;
+    if (atomicAdd(counters + 1, 1u) == total - 1) { counters[0] = 0u; counters[1] = 0u; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_cprow: compressed-row MatMultAdd / MatMult [P376 MatMult_SeqAIJ compressed branch]: only the
 // cprow.nrows non-empty rows are touched (the off-diagonal block B has ~2% non-empty rows).
 // For MatMult (ADD = false) y has been zeroed by the caller.
@@ -786,6 +895,11 @@ struct b200_csr_s {
   int4   *d_xtiles = nullptr;
   int    *d_longrows = nullptr;
   int32_t nxtiles = 0, nlong = 0;
+  // warp-granular exact-order plan (k_wmerge): chunks, blocks of chunks, work counters
+  int4     *d_wchunks = nullptr;
+  int      *d_wblk = nullptr;
+  unsigned *d_wcounters = nullptr;
+  int32_t   nwchunks = 0, nwblk = 0;
   // optional SELL-32-sigma copy (b200_csr_build_sell)
   double        *d_sval = nullptr;
   int           *d_scol = nullptr, *d_sperm = nullptr;
@@ -1005,6 +1119,50 @@ static int build_mergex_plan(b200_csr_s *A, const int32_t *ai)
   return B200_OK;
 }
 
+// Chunks and work blocks of k_wmerge.  A chunk holds whole rows while they fit WM_CAP non-zeros (and
+// at most WM_CAP rows: runs of empty rows); a row longer than WM_CAP becomes pieces of WM_CAP.  A work
+// block is ~WM_BLOCK consecutive chunks and never separates the pieces of one row.
+#define WM_BLOCK 16
+static int build_wmerge_plan(b200_csr_s *A, const int32_t *ai)
+{
+  const int m = A->m;
+  std::vector<int4> chunks;
+  std::vector<int>  blk;
+  chunks.reserve((size_t)A->nz / (WM_CAP / 2) + 16);
+  int r = 0;
+  while (r < m) {
+    const int len = ai[r + 1] - ai[r];
+    if (len > WM_CAP) {
+      for (int k = ai[r]; k < ai[r + 1]; k += WM_CAP) {
+        const int k1 = std::min(k + WM_CAP, ai[r + 1]);
+        chunks.push_back(make_int4(r, k == ai[r] ? -2 : (k1 == ai[r + 1] ? -3 : -1), k, k1));
+      }
+      ++r;
+      continue;
+    }
+    int rr = r;
+    while (rr < m && (rr - r) < WM_CAP && ai[rr + 1] - ai[rr] <= WM_CAP && ai[rr + 1] - ai[r] <= WM_CAP) ++rr;
+    chunks.push_back(make_int4(r, rr - r, ai[r], ai[rr]));
+    r = rr;
+  }
+  blk.push_back(0);
+  for (size_t c = 0; c < chunks.size();) {
+    size_t e = std::min(chunks.size(), c + WM_BLOCK);
+    while (e < chunks.size() && (chunks[e].y == -1 || chunks[e].y == -3)) ++e;   // keep a long row in one block
+    blk.push_back((int)e);
+    c = e;
+  }
+  A->nwchunks = (int)chunks.size();
+  A->nwblk    = (int)blk.size() - 1;
+  B200_TRY(dev_alloc(&A->d_wchunks, chunks.size(), A));
+  B200_TRY(dev_alloc(&A->d_wblk, blk.size(), A));
+  B200_TRY(dev_alloc(&A->d_wcounters, 2, A));
+  if (!chunks.empty()) B200_CUDA_TRY(cudaMemcpy(A->d_wchunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  B200_CUDA_TRY(cudaMemcpy(A->d_wblk, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice));
+  B200_CUDA_TRY(cudaMemset(A->d_wcounters, 0, 2 * sizeof(unsigned)));
+  return B200_OK;
+}
+
 // Build the plan from the host row-pointer array.
 static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
 {
@@ -1138,6 +1296,7 @@ static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
     // the same matrices in EXACT mode: whole-row tiles summed in CSR order (+ a warp per very long row)
     if (!A->cprow_use && !(A->ntiles && regular)) {
       B200_TRY(build_mergex_plan(A, ai));
+      B200_TRY(build_wmerge_plan(A, ai));
       if (A->nxtiles || A->nlong) A->kernel_exact = B200_KERNEL_MERGE;
     }
   } else A->kernel_fast = B200_KERNEL_ROW;
@@ -1307,6 +1466,7 @@ extern "C" int b200_csr_destroy(b200_csr_t A)
   cudaFree(A->d_aj8); cudaFree(A->d_offs);
   cudaFree(A->d_mtiles); cudaFree(A->d_msplit); cudaFree(A->d_mhead); cudaFree(A->d_mtail);
   cudaFree(A->d_xtiles); cudaFree(A->d_longrows);
+  cudaFree(A->d_wchunks); cudaFree(A->d_wblk); cudaFree(A->d_wcounters);
   sell_drop(A);
   cudaFree(A->d_hx); cudaFree(A->d_hy);
   for (auto &s : A->hs) if (s) cudaStreamDestroy(s);
@@ -1345,6 +1505,7 @@ extern "C" int b200_csr_set_kernel(b200_csr_t A, int kernel)
     B200_CUDA_TRY(cudaMemcpy(ai.data(), A->d_ai, ai.size() * sizeof(int), cudaMemcpyDeviceToHost));
     B200_TRY(build_merge_plan(A, ai.data()));
     if (!A->nmtiles) return set_error(B200_ERR_STATE, "merge kernel not applicable (empty matrix)");
+    if (!A->nwblk) B200_TRY(build_wmerge_plan(A, ai.data()));   // the exact-order form of the same override
   }
   A->kernel_override = kernel;
   return B200_OK;
@@ -1639,9 +1800,18 @@ static int spmv_dispatch(b200_csr_s *A, const double *x, const double *yin, doub
   // Skewed matrices: the exact-order kernels (whole-row tiles + a warp per long row) are also the
   // fastest measured (configs[4]: 1.08 ms vs 1.23 ms for the split-row merge), so FAST uses them too;
   // B200_MERGE_SPLIT=1 keeps the split-row merge kernel reachable for comparison.
-  const bool have_exact_plan = A->nxtiles || A->nlong;
+  const bool have_exact_plan = A->nxtiles || A->nlong || A->nwblk;
   if (kernel == B200_KERNEL_MERGE && (mode != B200_MODE_FAST || (have_exact_plan && !env_int("B200_MERGE_SPLIT", 0)))) {
     if (!have_exact_plan) return set_error(B200_ERR_ARG, "no exact-order merge plan for this matrix");
+    if (A->nwblk && env_int("B200_WMERGE", 1)) {
+      // persistent warps: as many CTAs as fit (8 warps, ~13-21 KB of shared memory each)
+      const int grid = std::max(1, std::min(sm_count() * 6, (A->nwblk + WM_WARPS - 1) / WM_WARPS));
+      if (mode == B200_MODE_EXACT_FMA)
+        B200_LAUNCH((k_wmerge<B200_MODE_EXACT_FMA, ADD>), grid, WM_WARPS * 32, 0, st, A->d_wchunks, A->d_wblk, A->nwblk, A->d_wcounters, A->d_ai, A->d_aj, A->d_aa, x, yin, y);
+      else
+        B200_LAUNCH((k_wmerge<B200_MODE_EXACT, ADD>), grid, WM_WARPS * 32, 0, st, A->d_wchunks, A->d_wblk, A->nwblk, A->d_wcounters, A->d_ai, A->d_aj, A->d_aa, x, yin, y);
+      return B200_OK;
+    }
 #define B200_MERGEX(MODE_)                                                                                   \
     do {                                                                                                     \
       if (A->nxtiles) B200_LAUNCH((k_mergex<MODE_, ADD>), A->nxtiles, MERGE_THREADS, 0, st, A->d_xtiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y); \
@@ -1946,6 +2116,26 @@ static bool host_pipeline_applies(b200_csr_s *A, int mode)
   const int kernel = A->kernel_override ? A->kernel_override : (mode == B200_MODE_FAST ? A->kernel_fast : A->kernel_exact);
   return kernel == B200_KERNEL_STREAM;
 }
+
+namespace b200 {
+int host_block_count(b200_csr_t A, int mode)
+{
+  return host_pipeline_applies(A, mode) ? (int)A->pb_tile.size() - 1 : 0;
+}
+int host_block_info(b200_csr_t A, int b, int *row0, int *row1, int *need)
+{
+  *row0 = A->h_tiles[A->pb_tile[b]].x;
+  *row1 = A->h_tiles[A->pb_tile[b + 1] - 1].y;
+  *need = std::max(A->pb_need[b], b);
+  return B200_OK;
+}
+int launch_host_block(b200_csr_t A, int b, const double *x, double *y, int mode, cudaStream_t st)
+{
+  const int t0 = A->pb_tile[b], nt = A->pb_tile[b + 1] - t0;
+  if (mode == B200_MODE_EXACT) return launch_stream_range<B200_MODE_EXACT, false>(A, t0, nt, x, nullptr, y, st);
+  return launch_stream_range<B200_MODE_EXACT_FMA, false>(A, t0, nt, x, nullptr, y, st);
+}
+}  // namespace b200
 
 extern "C" int b200_spmv_host(b200_csr_t A, const double *h_x, double *h_y, int mode)
 {

@@ -29,6 +29,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     pk.init(local)
+    os.environ.setdefault("B200_HOST_BLOCK_ROWS", "8192")     # several row blocks even on a small grid
     g = pk.gen_poisson7(N, world, rank)
     base = g["base"]
     M = pk.MpiAij(world, rank, base, g["ai"], g["aj"], g["aa"])
@@ -58,6 +59,16 @@ def main():
     if M.nghost:
         ref = oracle.matmultadd(Bi, Bj, Ba, xg[garrays[rank]], ref)
     first_ok = bool(np.array_equal(ref, y0.cpu().numpy()))
+    # the host-vector entry (row-blocked pipeline: uploads, block kernels, downloads and the ghost-row
+    # patch overlap): same bits, several times in a row
+    hx, hy = pk.PinnedArray(M.nloc), pk.PinnedArray(M.nloc)
+    hx.array[:] = xg[base[rank]:base[rank + 1]]
+    host_ok = True
+    for _ in range(5):
+        hy.array[:] = np.nan
+        M.mult_host(hx.array, hy.array, pk.MODE_EXACT)
+        host_ok = host_ok and bool(np.array_equal(ref, hy.array))
+    first_ok = first_ok and host_ok
     dist.barrier()
     # ranks are deliberately skewed: odd ranks do extra local work every few steps
     junk = torch.zeros(1 << 20, dtype=torch.float64, device=dev)

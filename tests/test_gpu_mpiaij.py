@@ -112,45 +112,57 @@ def test_flag_timeout_is_reported_not_hung(pk, cuda, monkeypatch):
         m.destroy()
 
 
-def test_distributed_cg_two_gpus(pk, cuda):
-    """KSPCG + PCJACOBI over two ranks (fused MatMult_MPIAIJ + peer-window all-reduce): same
-    iteration count on every rank, within one of the single-rank oracle CG, error at O(h^2)."""
-    import json
+def _torchrun(nproc, script, *args, timeout=600):
     import os
     import subprocess
     import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "tests", script), *[str(a) for a in args]]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    import json
+    return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+
+
+def test_two_gpus_distributed_cg_and_halo_stress(pk, cuda):
+    """Two real ranks (torchrun, one process per GPU, NVLink peer windows).
+    1. KSPCG + PCJACOBI (fused MatMult_MPIAIJ with (p, A p) folded in + peer-window all-reduces, no host
+       round trip): same iteration count on every rank and equal to the single-rank oracle CG's, error O(h^2).
+    2. Halo stress (tests/mpiaij_stress_worker.py): thousands of unsynchronised MatMults with a
+       different x each, skewed ranks, every result checked; the host-vector pipeline against the oracle.
+    The 8-GPU runs of the same workers are logged under profiles/."""
     torch = cuda
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     N = 24
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "tests", "mpiaij_cg_worker.py"), str(N), "1e-10"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
-    r = json.loads(line)
+    r = _torchrun(2, "mpiaij_cg_worker.py", N, "1e-10", timeout=300)
     p = oracle.poisson7(N)
     _, its, _ = oracle.cg_jacobi(p["ai"], p["aj"], p["aa"], p["rhs"], rtol=1e-10, atol=1e-50, max_it=20000)
     assert r["allreduce_ok"] and r["reason"] > 0
     assert len(set(r["its_all"])) == 1 and r["its"] == its, (r, its)
     assert r["linf_err"] < 0.02
+    s = _torchrun(2, "mpiaij_stress_worker.py", 40, 3000)
+    assert s["first_result_equals_oracle"] and s["mismatches"] == 0, s
 
 
-def test_halo_stress_two_gpus(cuda):
-    """Thousands of unsynchronised MatMults with a different x each, skewed ranks, every result
-    checked (tests/mpiaij_stress_worker.py); the 8-GPU run of the same worker is logged under profiles/."""
-    import json
-    import os
-    import subprocess
-    import sys
-    torch = cuda
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(29700 + os.getpid() % 200), os.path.join(root, "tests", "mpiaij_stress_worker.py"), "40", "3000"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-    assert r["first_result_equals_oracle"] and r["mismatches"] == 0, r
+def test_host_vector_pipeline_on_one_rank(pk, cuda, monkeypatch):
+    """b200_mpiaij_mult_host on a one-rank 'partition' (no ghosts): the row-blocked pipeline of uploads,
+    block kernels and downloads gives the bits of the oracle (several blocks forced on a small grid)."""
+    monkeypatch.setenv("B200_HOST_BLOCK_ROWS", "8192")
+    g = pk.gen_poisson7(40, 1, 0)
+    M = pk.MpiAij(1, 0, g["base"], g["ai"], g["aj"], g["aa"])
+    M.upload()
+    x = gen.uniform_pm1(M.nloc, 9)
+    hx, hy = pk.PinnedArray(M.nloc), pk.PinnedArray(M.nloc)
+    hx.array[:] = x
+    ref = oracle.matmult(g["ai"], g["aj"], g["aa"], x)
+    for mode, fma in ((pk.MODE_EXACT, False), (pk.MODE_EXACT_FMA, True)):
+        hy.array[:] = np.nan
+        M.mult_host(hx.array, hy.array, mode)
+        assert np.array_equal(hy.array, oracle.matmult(g["ai"], g["aj"], g["aa"], x, fma=fma))
+    monkeypatch.setenv("B200_MPIAIJ_HOST_PIPELINE", "0")
+    hy.array[:] = np.nan
+    M.mult_host(hx.array, hy.array, pk.MODE_EXACT)
+    assert np.array_equal(hy.array, ref)
+    M.destroy()
