@@ -224,26 +224,49 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // releases that peer's flag
 // NT > 0: only the first NT threads of the CTA take part (the consumer threads of k_stream; they
 // meet on named barrier 1); NT == 0: the whole CTA.
+// Two steps, so that the fused kernel can put a tile of useful work between them:
+//   stores  every thread writes its share of the boundary values into the peer's lvec (posted NVLink
+//           writes) and carries on;
+//   signal  the CTA's threads meet on a barrier (their stores happen-before thread 0 from here on),
+//           thread 0 alone runs the system-scope fence -- cumulative: it orders everything that
+//           happened before it, the pattern of a cooperative grid barrier -- and counts the block in;
+//           the last block of a peer releases that peer's flag.  By then the write acknowledgements
+//           have long arrived, so the fence does not stall the way it does right behind the stores.
 template <int NT>
-__device__ __forceinline__ void halo_push_block(const HaloArgs &h, const double *__restrict__ x, int block)
+__device__ __forceinline__ void halo_push_stores(const HaloArgs &h, const double *__restrict__ x, int block)
 {
   const PushBlock b   = h.blocks[block];
   const PushPeer  p   = h.peers[b.peer_slot];
-  double         *dst = p.dst[h.seq & 1];
+  double         *dst = (h.seq & 1) ? p.dst[1] : p.dst[0];
   const int       nt  = NT > 0 ? NT : (int)blockDim.x;
-  for (int t = threadIdx.x; t < b.count; t += nt) {
-    const int e = b.start + t;
-    dst[e]      = __ldg(x + h.send_idx[e]);
+  // four elements per thread and round: the index loads, then the gathers, then the stores of a round
+  // are in flight together (a push block of the fused launch carries thousands of elements)
+#pragma unroll 1
+  for (int t0 = threadIdx.x; t0 < b.count; t0 += 4 * nt) {
+    int    idx[4];
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) idx[j] = (t0 + j * nt < b.count) ? __ldg(h.send_idx + b.start + t0 + j * nt) : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(x + idx[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (t0 + j * nt < b.count) dst[b.start + t0 + j * nt] = v[j];
   }
-  __threadfence_system();
+}
+template <int NT>
+__device__ __forceinline__ void halo_push_signal(const HaloArgs &h, int block)
+{
   if (NT > 0) asm volatile("bar.sync 1, %0;" ::"n"(NT > 0 ? NT : 32) : "memory");
   else __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(h.done + b.peer_slot, 1u);
-    if (prev == (unsigned)p.nblocks - 1) {
-      h.done[b.peer_slot] = 0;
+    const int peer_slot = h.blocks[block].peer_slot;
+    __threadfence_system();
+    const unsigned prev = atomicAdd(h.done + peer_slot, 1u);
+    if (prev == (unsigned)h.peers[peer_slot].nblocks - 1) {
+      h.done[peer_slot] = 0;
       __threadfence_system();
-      st_release_sys(p.flag, h.seq);
+      st_release_sys(h.peers[peer_slot].flag, h.seq);
     }
   }
 }

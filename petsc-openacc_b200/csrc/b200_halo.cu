@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256)
 {
   HaloArgs h{};
   h.blocks = blocks; h.peers = peers; h.send_idx = send_idx; h.done = done; h.seq = seq;
-  halo_push_block<0>(h, x, blockIdx.x);
+  halo_push_stores<0>(h, x, blockIdx.x);
+  halo_push_signal<0>(h, blockIdx.x);
 }
 
 // pack only (transport owned by the caller)
@@ -326,6 +327,27 @@ static int up(T **d, const std::vector<T> &h)
   return B200_OK;
 }
 
+// Elements per push block of the fused launch.  Measured on 8 B200s (profiles/r02_halo_attribution.md):
+// with one push block on every SM the stores to peer memory and the system-scope fences behind them
+// cost the launch 7 us of its 48; concentrated on a few CTAs -- which the tile schedule then gives
+// fewer tiles -- the other ~720 CTAs never touch NVLink.  B200_MPIAIJ_PUSH_CTAS (default 16) blocks,
+// at least one per destination.
+static int fused_push_chunk(b200_mpiaij_s *M, int grid)
+{
+  long long total = 0;
+  for (auto &s : M->sends) total += s.count;
+  const int want = std::max(1, std::min(env_int("B200_MPIAIJ_PUSH_CTAS", 16), grid / 4));
+  const int room = std::max(1, want - (int)M->sends.size());
+  return (int)std::max<long long>(256, ((total + room - 1) / room + 255) / 256 * 256);
+}
+static int fused_push_blocks(b200_mpiaij_s *M, int grid)
+{
+  const int chunk = fused_push_chunk(M, grid);
+  int n = 0;
+  for (auto &s : M->sends) n += (s.count + chunk - 1) / chunk;
+  return n;
+}
+
 extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
 {
   NvtxRange nvtx_("b200_mpiaij_upload");
@@ -379,7 +401,11 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
       if (lpt) {
         using Load = std::pair<double, int>;
         std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-        for (int b = 0; b < grid; ++b) heap.push({0.0, b});
+        // the first CTAs also carry a push block (send lists as known now): VecScatterBegin's stores and
+        // the fence behind them are charged like B200_MPIAIJ_PUSH_CHARGE_TENTHS / 10 tiles
+        const int    npush = std::min(grid, fused_push_blocks(M, grid));
+        const double push_charge = env_int("B200_MPIAIJ_PUSH_CHARGE_TENTHS", 40) / 10.0;
+        for (int b = 0; b < grid; ++b) heap.push({b < npush ? push_charge : 0.0, b});
         auto deal = [&](int t) {
           Load top = heap.top();
           heap.pop();
@@ -507,13 +533,7 @@ static int prepare_push(b200_mpiaij_s *M)
   M->send_start.clear();
   // fused launch: one push block per SM (the first wave places CTA b on SM b), so that each SM
   // executes a single system-scope release fence; stand-alone push kernel: PUSH_CHUNK per CTA
-  int chunk = PUSH_CHUNK;
-  if (M->fused_ok) {
-    long long total = 0;
-    for (auto &s : M->sends) total += s.count;
-    const int room = std::max(1, std::min(M->fused_grid, sm_count()) - (int)M->sends.size());
-    chunk = (int)std::max<long long>(64, ((total + room - 1) / room + 31) / 32 * 32);
-  }
+  const int chunk = M->fused_ok ? fused_push_chunk(M, M->fused_grid) : PUSH_CHUNK;
   int slot = 0;
   for (auto &s : M->sends) {
     if (!s.peer_window) return set_error(B200_ERR_STATE, "peer %d needs data but its window is not mapped", s.peer);
@@ -593,6 +613,10 @@ static HaloArgs fused_args(b200_mpiaij_s *M, bool with_push)
   h.lvec = (const double *)(M->d_window + WINDOW_HDR_BYTES) + (size_t)(M->seq & 1) * M->ngpad;
   h.flags = (const unsigned long long *)M->d_window; h.srcs = M->d_srcs; h.nsrc = (int)M->srcs.size();
   h.seq = M->seq; h.err = (unsigned long long *)M->d_window + ERR_WORD; h.timeout_ns = M->timeout_ns;
+  // timing probes (results are then WRONG): no VecScatterBegin stores / no wait for the peers' flags
+  static const int probe_nopush = env_int("B200_MPIAIJ_PROBE_NOPUSH", 0), probe_nowait = env_int("B200_MPIAIJ_PROBE_NOWAIT", 0);
+  if (probe_nopush) h.npush = 0;
+  if (probe_nowait) h.nsrc = 0;
   return h;
 }
 

@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
       // column positions, values -- all constant) into L2, so that the dependent loads at the very end
       // of the CTA, which sit on the critical path of the launch, are L2 hits instead of DRAM round trips.
       const int q0 = __ldg(h.cta_ptr + bid), q1 = __ldg(h.cta_ptr + bid + 1);
+#pragma unroll 1
       for (int q = q0 + (tid - THREADS - 1); q < q1; q += 31) {
         const int c  = __ldg(h.cta_rows + q);
         const int lo = __ldg(h.cpi + c);
@@ -339,7 +340,11 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
 
   // --------------------------------- consumers -------------------------------------------------
   pdl_wait();
-  if (HALO && bid < h.npush) halo_push_block<THREADS>(h, x, bid);
+  // VecScatterBegin: the stores go out now; the fence + flag release follow a tile or two later, when
+  // the write acknowledgements are back and the fence is cheap (the peers need the flag at THEIR end)
+  const bool pusher = HALO && bid < h.npush;
+  if (pusher) halo_push_stores<THREADS>(h, x, bid);
+  const int signal_at = (tile1 - tile0 > tstep) ? 1 : 0;
   double dacc = 0.0;
   int it = 0;
   for (int tile = tile0; tile < tile1; tile += tstep, ++it) {
@@ -381,6 +386,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    if (pusher && it == signal_at) halo_push_signal<THREADS>(h, bid);
   }
   if (HALO) {
     // one lane per source rank waits for that rank's flag; the consumer-only barrier publishes the
@@ -388,17 +394,21 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     if (tid < h.nsrc) {
       const unsigned long long t0 = globaltimer_ns();
       const unsigned long long *f = h.flags + h.srcs[tid];
+#pragma unroll 1
       while (ld_relaxed_sys(f) < h.seq) {
         if (globaltimer_ns() - t0 > h.timeout_ns) { atomicExch(h.err, 1ull); break; }
         __nanosleep(32);
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+    // (the closing loops are kept rolled: the kernel's code must stay well inside the instruction cache)
+#pragma unroll 1
     for (int q = h.cta_ptr[bid] + tid; q < h.cta_ptr[bid + 1]; q += THREADS) {
       const int c  = h.cta_rows[q];
       const int lo = h.cpi[c], hi = h.cpi[c + 1], i = h.ridx[c];
       const double s0 = y[i];
       double    sb = s0;
+#pragma unroll 1
       for (int k = lo; k < hi; ++k) sb = acc<MODE>(sb, h.ba[k], __ldcg(h.lvec + h.bj[k]));
       y[i] = sb;
       if (EPI == EPI_DOT) dacc = __fma_rn(__ldg(x + i), __dsub_rn(sb, s0), dacc);   // the ghost terms' share of (x, y)
@@ -427,6 +437,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
       if (last) {
         __threadfence();
         double t = 0.0;
+#pragma unroll 1
         for (int q = tid; q < nb; q += 32) t += __ldcg(dot.partials + q);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
