@@ -239,18 +239,19 @@ __device__ __forceinline__ void halo_push_stores(const HaloArgs &h, const double
   const PushPeer  p   = h.peers[b.peer_slot];
   double         *dst = (h.seq & 1) ? p.dst[1] : p.dst[0];
   const int       nt  = NT > 0 ? NT : (int)blockDim.x;
-  // four elements per thread and round: the index loads, then the gathers, then the stores of a round
-  // are in flight together (a push block of the fused launch carries thousands of elements)
+  // eight elements per thread and round: the index loads, then the gathers, then the stores of a round
+  // are in flight together (a push block of the fused launch carries a few thousand elements)
+  constexpr int R = 8;
 #pragma unroll 1
-  for (int t0 = threadIdx.x; t0 < b.count; t0 += 4 * nt) {
-    int    idx[4];
-    double v[4];
+  for (int t0 = threadIdx.x; t0 < b.count; t0 += R * nt) {
+    int    idx[R];
+    double v[R];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) idx[j] = (t0 + j * nt < b.count) ? __ldg(h.send_idx + b.start + t0 + j * nt) : 0;
+    for (int j = 0; j < R; ++j) idx[j] = (t0 + j * nt < b.count) ? __ldg(h.send_idx + b.start + t0 + j * nt) : 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __ldg(x + idx[j]);
+    for (int j = 0; j < R; ++j) v[j] = __ldg(x + idx[j]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < R; ++j)
       if (t0 + j * nt < b.count) dst[b.start + t0 + j * nt] = v[j];
   }
 }

@@ -330,13 +330,13 @@ static int up(T **d, const std::vector<T> &h)
 // Elements per push block of the fused launch.  Measured on 8 B200s (profiles/r02_halo_attribution.md):
 // with one push block on every SM the stores to peer memory and the system-scope fences behind them
 // cost the launch 7 us of its 48; concentrated on a few CTAs -- which the tile schedule then gives
-// fewer tiles -- the other ~720 CTAs never touch NVLink.  B200_MPIAIJ_PUSH_CTAS (default 16) blocks,
+// fewer tiles -- the other ~700 CTAs never touch NVLink.  B200_MPIAIJ_PUSH_CTAS (default 32) blocks,
 // at least one per destination.
 static int fused_push_chunk(b200_mpiaij_s *M, int grid)
 {
   long long total = 0;
   for (auto &s : M->sends) total += s.count;
-  const int want = std::max(1, std::min(env_int("B200_MPIAIJ_PUSH_CTAS", 16), grid / 4));
+  const int want = std::max(1, std::min(env_int("B200_MPIAIJ_PUSH_CTAS", 32), grid / 4));
   const int room = std::max(1, want - (int)M->sends.size());
   return (int)std::max<long long>(256, ((total + room - 1) / room + 255) / 256 * 256);
 }
@@ -404,7 +404,8 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
         // the first CTAs also carry a push block (send lists as known now): VecScatterBegin's stores and
         // the fence behind them are charged like B200_MPIAIJ_PUSH_CHARGE_TENTHS / 10 tiles
         const int    npush = std::min(grid, fused_push_blocks(M, grid));
-        const double push_charge = env_int("B200_MPIAIJ_PUSH_CHARGE_TENTHS", 40) / 10.0;
+        // (never more than would leave a push CTA without a tile of its own)
+        const double push_charge = std::min(env_int("B200_MPIAIJ_PUSH_CHARGE_TENTHS", 40) / 10.0, std::max(0.0, (double)(ntiles / grid) - 1.0));
         for (int b = 0; b < grid; ++b) heap.push({b < npush ? push_charge : 0.0, b});
         auto deal = [&](int t) {
           Load top = heap.top();
@@ -425,8 +426,18 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
         std::vector<int> next(first.begin(), first.end() - 1);
         for (int t = 0; t < ntiles; ++t) sched_tiles[next[cta_of[t]]++] = tiles[t];   // ascending inside a CTA
       }
-      for (int b = 0; b < grid; ++b)
-        if (first[b + 1] == first[b]) return set_error(B200_ERR_STATE, "tile schedule left CTA %d without work", b);
+      bool starved = false;
+      for (int b = 0; b < grid; ++b) starved = starved || first[b + 1] == first[b];
+      if (starved) {
+        // (tiny matrices: the charges can leave a CTA without a tile; every CTA of the launch must
+        // own at least one) -- plain round-robin
+        for (int t = 0; t < ntiles; ++t) cta_of[t] = t % grid;
+        std::fill(first.begin(), first.end(), 0);
+        for (int t = 0; t < ntiles; ++t) first[cta_of[t] + 1]++;
+        for (int b = 0; b < grid; ++b) first[b + 1] += first[b];
+        std::vector<int> next(first.begin(), first.end() - 1);
+        for (int t = 0; t < ntiles; ++t) sched_tiles[next[cta_of[t]]++] = tiles[t];
+      }
       std::vector<int> owner(M->ridx.size()), ptr((size_t)grid + 1, 0), rows(M->ridx.size());
       for (size_t c = 0; c < M->ridx.size(); ++c) {
         owner[c] = cta_of[tile_of[c]];
