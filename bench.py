@@ -388,7 +388,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     kname = pk.KERNEL_NAMES[info.kernel_fast if mode == pk.MODE_FAST else info.kernel_exact]
     if kname == "merge":
-        kname = "mergex + k_longrow"
+        kname = "wmerge"
     stream_bytes = nnz * (9 if info.index8_diagonals else 12) + m * 20
     roof = {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": peak, "unit": "GB/s",
             "frac": nbytes / ms / 1e6 / peak,

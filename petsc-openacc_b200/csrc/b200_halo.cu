@@ -402,10 +402,12 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
         using Load = std::pair<double, int>;
         std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
         // the first CTAs also carry a push block (send lists as known now): VecScatterBegin's stores and
-        // the fence behind them are charged like B200_MPIAIJ_PUSH_CHARGE_TENTHS / 10 tiles
+        // the fence behind them are charged like B200_MPIAIJ_PUSH_CHARGE_TENTHS / 10 tiles (default 6.0:
+        // 8 GPUs, 32 push CTAs: 46.5 us per MatMult at 4.0, 45.2 at 6.0; 16 CTAs / 8.0: 48.8; one block per
+        // SM / 1.0: 48.1 -- profiles/r02_halo_attribution.md)
         const int    npush = std::min(grid, fused_push_blocks(M, grid));
         // (never more than would leave a push CTA without a tile of its own)
-        const double push_charge = std::min(env_int("B200_MPIAIJ_PUSH_CHARGE_TENTHS", 40) / 10.0, std::max(0.0, (double)(ntiles / grid) - 1.0));
+        const double push_charge = std::min(env_int("B200_MPIAIJ_PUSH_CHARGE_TENTHS", 60) / 10.0, std::max(0.0, (double)(ntiles / grid) - 1.0));
         for (int b = 0; b < grid; ++b) heap.push({b < npush ? push_charge : 0.0, b});
         auto deal = [&](int t) {
           Load top = heap.top();
@@ -446,7 +448,6 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
       for (int b = 0; b < grid; ++b) ptr[b + 1] += ptr[b];
       std::vector<int> next(ptr.begin(), ptr.end() - 1);
       for (size_t c = 0; c < M->ridx.size(); ++c) rows[next[owner[c]]++] = (int)c;
-      if (env_int("B200_MPIAIJ_PROBE_NOGHOST", 0)) std::fill(ptr.begin(), ptr.end(), 0);   // timing probe only: wrong results
       B200_TRY(up(&M->d_cta_ptr, ptr));
       B200_TRY(up(&M->d_cta_rows, rows));
       if (lpt) {
@@ -542,8 +543,8 @@ static int prepare_push(b200_mpiaij_s *M)
   std::vector<PushBlock> blocks;
   std::vector<PushPeer>  peers;
   M->send_start.clear();
-  // fused launch: one push block per SM (the first wave places CTA b on SM b), so that each SM
-  // executes a single system-scope release fence; stand-alone push kernel: PUSH_CHUNK per CTA
+  // fused launch: a few dozen push blocks on the first CTAs (fused_push_chunk); stand-alone push
+  // kernel: PUSH_CHUNK elements per CTA
   const int chunk = M->fused_ok ? fused_push_chunk(M, M->fused_grid) : PUSH_CHUNK;
   int slot = 0;
   for (auto &s : M->sends) {
@@ -624,10 +625,6 @@ static HaloArgs fused_args(b200_mpiaij_s *M, bool with_push)
   h.lvec = (const double *)(M->d_window + WINDOW_HDR_BYTES) + (size_t)(M->seq & 1) * M->ngpad;
   h.flags = (const unsigned long long *)M->d_window; h.srcs = M->d_srcs; h.nsrc = (int)M->srcs.size();
   h.seq = M->seq; h.err = (unsigned long long *)M->d_window + ERR_WORD; h.timeout_ns = M->timeout_ns;
-  // timing probes (results are then WRONG): no VecScatterBegin stores / no wait for the peers' flags
-  static const int probe_nopush = env_int("B200_MPIAIJ_PROBE_NOPUSH", 0), probe_nowait = env_int("B200_MPIAIJ_PROBE_NOWAIT", 0);
-  if (probe_nopush) h.npush = 0;
-  if (probe_nowait) h.nsrc = 0;
   return h;
 }
 

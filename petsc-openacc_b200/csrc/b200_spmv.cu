@@ -10,15 +10,22 @@
 //
 // Kernels (all fp64 values, int32 indices):
 //   k_stream  bulk-copy staged CSR tiles, thread per row -- default for short, regular rows; template
-//             flags: EPI (MatMult / MatMultAdd / residual / Jacobi sweep), HALO (MatMult_MPIAIJ in one
-//             launch: NVLink push + A x + ghost rows), IDX8 (1-byte diagonal codes instead of int32 columns)
-//   k_merge   nnz-balanced tiles + deterministic carry fix-up -- skewed row lengths
+//             flags: EPI (MatMult / MatMultAdd / residual / Jacobi sweep / MatMult + CG's (p, A p)), HALO
+//             (MatMult_MPIAIJ in one launch: NVLink push + A x + ghost rows), IDX8 (1-byte diagonal codes
+//             instead of int32 columns); launched with programmatic stream serialization: the set-up
+//             and the first bulk copies of the constant matrix run under the previous kernel's tail
+//   k_wmerge  warp-granular chunks of <= 128 non-zeros, products staged coalesced, rows summed in
+//             CSR order, persistent warps drawing work from a counter -- skewed row lengths (power law),
+//             EXACT and FAST
+//   k_merge   nnz-balanced tiles + deterministic carry fix-up, lanes share a row -- B200_MERGE_SPLIT=1 only
 //   k_row     thread per row from global memory          -- the reference's launch shape; EXACT fallback
 //   k_vector  LANES lanes per row + __shfl_xor reduction -- override / comparison
 //   k_cprow   compressed-row (only non-empty rows)       -- matrices with >= 60 % empty rows
 //   k_tr_atomic  A^T x by fp64 atomics                   -- transpose without a second copy
 //   k_sell    SELL-32-sigma copy (optional, b200_csr_build_sell), column-major chunks of 32 rows,
-//             padding skipped -- override only; not yet measured against k_stream
+//             padding skipped -- override only: measured 0.456 ms against k_stream's 0.332 ms on the
+//             7-point 300^3 matrix and 0.431 against 0.356 ms on the 27-point 200^3 matrix
+//             (profiles/r02_sweep_*.log)
 // Why the SELL-C-sigma / sliced-ELL copy is not the default: staging the CSR tile in shared memory
 // already gives what those formats buy on a GPU -- the matrix is read in fully coalesced
 // 16-byte-aligned bulk copies and lane = consecutive row makes the x gathers of a stencil
@@ -462,7 +469,6 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
 #define MERGE_CAP 2048
 #define MERGE_RCAP 1024
 #define MERGE_THREADS 256
-#define MERGEX_LONG 96
 
 template <bool ADD>
 __global__ void __launch_bounds__(MERGE_THREADS)
@@ -532,104 +538,6 @@ __global__ void k_merge_fixup(int nsplit, const int4 *__restrict__ split, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_mergex / k_longrow: the EXACT summation order on skewed matrices at merge-kernel speed.
-// Tiles hold WHOLE rows only (at most MERGE_CAP non-zeros, MERGE_RCAP rows); the CTA stages a and
-// x[aj] side by side in shared memory, coalesced over non-zeros, then one thread per row adds the
-// row left to right (unfused or fma, like the oracle).  Rows beyond MERGEX_LONG entries go to k_longrow:
-// one warp per row loads 32 (a, x) pairs at a time and every lane replays the 32 adds in order
-// through shuffles -- the chain is as long as on one thread, but the loads are coalesced.
-// xtiles[t] = {first row, last row + 1, ai[first], ai[last + 1]}.
-// ---------------------------------------------------------------------------------------------
-template <int MODE, bool ADD>
-__global__ void __launch_bounds__(MERGE_THREADS)
-    k_mergex(const int4 *__restrict__ tiles, const int *__restrict__ ii, const int *__restrict__ aj,
-             const double *__restrict__ aa, const double *__restrict__ x, const double *yin, double *y)
-{
-  // EXACT rounds the product on its own, so the product is what gets staged (half the shared
-  // memory, twice the CTAs per SM); EXACT_FMA needs a and x side by side for the fused chain
-  constexpr bool PROD = (MODE == B200_MODE_EXACT);
-  __shared__ double sa[MERGE_CAP];
-  __shared__ double sx[PROD ? 1 : MERGE_CAP];
-  __shared__ int    rp[MERGE_RCAP + 1];
-  const int4 d   = __ldg(tiles + blockIdx.x);
-  const int  tid = threadIdx.x, nr = d.y - d.x, s = d.z, n = d.w - d.z;
-  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-  for (int j = tid; j <= nr; j += MERGE_THREADS) rp[j] = __ldg(ii + d.x + j) - s;
-  {
-    constexpr int PER = MERGE_CAP / MERGE_THREADS;
-    int    c[PER];
-    double a[PER];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int k = tid + i * MERGE_THREADS;
-      c[i] = (k < n) ? ldg_s32_stream_policy(aj + s + k, pol_stream) : 0;
-      a[i] = (k < n) ? ldg_f64_stream_policy(aa + s + k, pol_stream) : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int k = tid + i * MERGE_THREADS;
-      if (k < n) {
-        const double xv = ldg_f64_policy(x + c[i], pol_keep);
-        if (PROD) sa[k] = __dmul_rn(a[i], xv);
-        else { sa[k] = a[i]; sx[k] = xv; }
-      }
-    }
-  }
-  __syncthreads();
-  for (int j = tid; j < nr; j += MERGE_THREADS) {
-    const int r   = d.x + j;
-    double    sum = ADD ? yin[r] : 0.0;
-    if (PROD) for (int k = rp[j]; k < rp[j + 1]; ++k) sum = __dadd_rn(sum, sa[k]);
-    else for (int k = rp[j]; k < rp[j + 1]; ++k) sum = __fma_rn(sa[k], sx[k], sum);
-    y[r] = sum;
-  }
-}
-
-// One warp per long row: the lanes fetch 32 (a, x) pairs at a time, coalesced, and park them (or
-// their rounded products) in shared memory; lane 0 alone runs the ordered chain out of shared
-// memory while the next 32 pairs are already in flight.  (Replaying the chain on all lanes through
-// shuffles was shuffle-throughput bound: 1.5 ms for the 46 M long-row entries of configs[4].)
-template <int MODE, bool ADD>
-__global__ void __launch_bounds__(128)
-    k_longrow(int nlong, const int *__restrict__ rows, const int *__restrict__ ii, const int *__restrict__ aj,
-              const double *__restrict__ aa, const double *__restrict__ x, const double *yin, double *y)
-{
-  constexpr bool PROD = (MODE == B200_MODE_EXACT);
-  __shared__ double sa[4][2][32];
-  __shared__ double sx[4][2][PROD ? 1 : 32];
-  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w  = blockIdx.x * 4 + wl;
-  if (w >= nlong) return;
-  const int r = rows[w], lo = ii[r], hi = ii[r + 1];
-  double    sum = ADD ? yin[r] : 0.0;
-  // matrix stream: read once (L2 evict-first); x: reused by every row (evict-last) -- without the
-  // hints this kernel's 46 M gathers pulled 2.1 GB from DRAM for 0.55 GB of matrix (ncu, round 1)
-  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-  int    k  = lo + lane;
-  double a  = (k < hi) ? ldg_f64_stream_policy(aa + k, pol_stream) : 0.0;
-  double xv = (k < hi) ? ldg_f64_policy(x + ldg_s32_stream_policy(aj + k, pol_stream), pol_keep) : 0.0;
-  int    buf = 0;
-  for (int base = lo; base < hi; base += 32, buf ^= 1) {
-    if (PROD) sa[wl][buf][lane] = __dmul_rn(a, xv);
-    else { sa[wl][buf][lane] = a; sx[wl][buf][lane] = xv; }
-    __syncwarp();
-    const int kn = base + 32 + lane;          // next chunk: in flight during the chain below
-    a  = (kn < hi) ? ldg_f64_stream_policy(aa + kn, pol_stream) : 0.0;
-    xv = (kn < hi) ? ldg_f64_policy(x + ldg_s32_stream_policy(aj + kn, pol_stream), pol_keep) : 0.0;
-    if (lane == 0) {
-      const int cnt = min(32, hi - base);
-      if (cnt == 32) {
-#pragma unroll
-        for (int l = 0; l < 32; ++l) sum = PROD ? __dadd_rn(sum, sa[wl][buf][l]) : __fma_rn(sa[wl][buf][l], sx[wl][buf][l], sum);
-      } else {
-        for (int l = 0; l < cnt; ++l) sum = PROD ? __dadd_rn(sum, sa[wl][buf][l]) : __fma_rn(sa[wl][buf][l], sx[wl][buf][l], sum);
-      }
-    }
-  }
-  if (lane == 0) y[r] = sum;
-}
-
-// ---------------------------------------------------------------------------------------------
 // k_wmerge: the exact summation order on skewed matrices, warp granular.  The matrix is cut into
 // CHUNKS of at most WM_CAP consecutive non-zeros: either a run of whole rows (each at most WM_CAP
 // long) or one piece of a longer row.  A warp stages a chunk -- column indices and values coalesced
@@ -637,9 +545,12 @@ __global__ void __launch_bounds__(128)
 // a and x side by side for the fused chain) in its own slice of shared memory, then its lanes sum
 // the chunk's rows left to right, one row per lane; a long row is summed by lane 0 chunk after
 // chunk with the partial sum carried in a register.  No block barrier, no tile is ever cut short by
-// a long row next to it (what left the block-granular k_mergex tiles a quarter full on the power-law
-// matrix), and persistent warps draw BLOCKS of consecutive chunks from an atomic counter, so a
-// 10,000-entry row delays one warp, not a CTA.
+// a long row next to it (what left the whole-row CTA tiles of round 1's k_mergex a quarter full on the
+// power-law matrix: 1.01 ms there, 0.856 ms here), and persistent warps draw BLOCKS of consecutive
+// chunks from an atomic counter, so a 10,000-entry row delays one warp, not a CTA.  At 115 G
+// non-zeros/s it runs at the rate this GPU gives to independent 8-byte gathers from an 80 MB vector:
+// the stream kernel on the (regular) transpose of the same matrix reaches the same 115, a bare
+// torch.index_select over the same index stream 148 (profiles/r02_powerlaw.md).
 // chunks[c] = {first row, rows (>= 0) | -1 middle / -2 first / -3 last piece of a long row, k0, k1}.
 // ---------------------------------------------------------------------------------------------
 #define WM_CAP 128
@@ -902,10 +813,6 @@ struct b200_csr_s {
   int4   *d_mtiles = nullptr, *d_msplit = nullptr;
   double *d_mhead = nullptr, *d_mtail = nullptr;
   int32_t nmtiles = 0, nmsplit = 0;
-  // exact-order merge plan: whole-row tiles + the rows longer than a tile
-  int4   *d_xtiles = nullptr;
-  int    *d_longrows = nullptr;
-  int32_t nxtiles = 0, nlong = 0;
   // warp-granular exact-order plan (k_wmerge): chunks, blocks of chunks, work counters
   int4     *d_wchunks = nullptr;
   int      *d_wblk = nullptr;
@@ -1105,31 +1012,6 @@ static int build_idx8(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
   return B200_OK;
 }
 
-// Whole-row tiles for the exact-order merge kernel; rows longer than MERGEX_LONG are listed apart.
-static int build_mergex_plan(b200_csr_s *A, const int32_t *ai)
-{
-  const int m = A->m;
-  std::vector<int4> tiles;
-  std::vector<int>  longrows;
-  int r = 0;
-  while (r < m) {
-    // a sequential chain costs ~8 cycles per entry: rows beyond MERGEX_LONG entries get a warp of
-    // their own (64 chains per SM in flight) instead of stalling a whole CTA behind one thread
-    if (ai[r + 1] - ai[r] > MERGEX_LONG) { longrows.push_back(r); ++r; continue; }
-    int rr = r;
-    while (rr < m && ai[rr + 1] - ai[r] <= MERGE_CAP && (rr - r) < MERGE_RCAP && ai[rr + 1] - ai[rr] <= MERGEX_LONG) ++rr;
-    tiles.push_back(make_int4(r, rr, ai[r], ai[rr]));
-    r = rr;
-  }
-  A->nxtiles = (int)tiles.size();
-  A->nlong   = (int)longrows.size();
-  B200_TRY(dev_alloc(&A->d_xtiles, tiles.size(), A));
-  B200_TRY(dev_alloc(&A->d_longrows, longrows.size(), A));
-  if (!tiles.empty()) B200_CUDA_TRY(cudaMemcpy(A->d_xtiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
-  if (!longrows.empty()) B200_CUDA_TRY(cudaMemcpy(A->d_longrows, longrows.data(), longrows.size() * sizeof(int), cudaMemcpyHostToDevice));
-  return B200_OK;
-}
-
 // Chunks and work blocks of k_wmerge.  A chunk holds whole rows while they fit WM_CAP non-zeros (and
 // at most WM_CAP rows: runs of empty rows); a row longer than WM_CAP becomes pieces of WM_CAP.  A work
 // block is ~WM_BLOCK consecutive chunks and never separates the pieces of one row.
@@ -1306,9 +1188,8 @@ static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
     A->kernel_fast = A->nmtiles ? B200_KERNEL_MERGE : B200_KERNEL_VECTOR;
     // the same matrices in EXACT mode: whole-row tiles summed in CSR order (+ a warp per very long row)
     if (!A->cprow_use && !(A->ntiles && regular)) {
-      B200_TRY(build_mergex_plan(A, ai));
       B200_TRY(build_wmerge_plan(A, ai));
-      if (A->nxtiles || A->nlong) A->kernel_exact = B200_KERNEL_MERGE;
+      if (A->nwblk) A->kernel_exact = B200_KERNEL_MERGE;
     }
   } else A->kernel_fast = B200_KERNEL_ROW;
   return B200_OK;
@@ -1476,7 +1357,6 @@ extern "C" int b200_csr_destroy(b200_csr_t A)
   cudaFree(A->d_cpi); cudaFree(A->d_ridx); cudaFree(A->d_tiles);
   cudaFree(A->d_aj8); cudaFree(A->d_offs);
   cudaFree(A->d_mtiles); cudaFree(A->d_msplit); cudaFree(A->d_mhead); cudaFree(A->d_mtail);
-  cudaFree(A->d_xtiles); cudaFree(A->d_longrows);
   cudaFree(A->d_wchunks); cudaFree(A->d_wblk); cudaFree(A->d_wcounters);
   sell_drop(A);
   cudaFree(A->d_hx); cudaFree(A->d_hy);
@@ -1808,28 +1688,18 @@ static int spmv_dispatch(b200_csr_s *A, const double *x, const double *yin, doub
   int kernel = A->kernel_override;
   if (!kernel) kernel = (mode == B200_MODE_FAST) ? A->kernel_fast : A->kernel_exact;
   if (kernel == B200_KERNEL_SELL) return launch_sell<ADD>(A, x, yin, y, mode, st);
-  // Skewed matrices: the exact-order kernels (whole-row tiles + a warp per long row) are also the
-  // fastest measured (configs[4]: 1.08 ms vs 1.23 ms for the split-row merge), so FAST uses them too;
-  // B200_MERGE_SPLIT=1 keeps the split-row merge kernel reachable for comparison.
-  const bool have_exact_plan = A->nxtiles || A->nlong || A->nwblk;
+  // Skewed matrices: the exact-order kernel is also the fastest measured (configs[4]: 0.86 ms vs
+  // 1.23 ms for the split-row merge), so FAST uses it too; B200_MERGE_SPLIT=1 keeps the split-row
+  // merge kernel reachable for comparison.
+  const bool have_exact_plan = A->nwblk > 0;
   if (kernel == B200_KERNEL_MERGE && (mode != B200_MODE_FAST || (have_exact_plan && !env_int("B200_MERGE_SPLIT", 0)))) {
     if (!have_exact_plan) return set_error(B200_ERR_ARG, "no exact-order merge plan for this matrix");
-    if (A->nwblk && env_int("B200_WMERGE", 1)) {
-      // persistent warps: as many CTAs as fit (8 warps, ~13-21 KB of shared memory each)
-      const int grid = std::max(1, std::min(sm_count() * 6, (A->nwblk + WM_WARPS - 1) / WM_WARPS));
-      if (mode == B200_MODE_EXACT_FMA)
-        B200_LAUNCH((k_wmerge<B200_MODE_EXACT_FMA, ADD>), grid, WM_WARPS * 32, 0, st, A->d_wchunks, A->d_wblk, A->nwblk, A->d_wcounters, A->d_ai, A->d_aj, A->d_aa, x, yin, y);
-      else
-        B200_LAUNCH((k_wmerge<B200_MODE_EXACT, ADD>), grid, WM_WARPS * 32, 0, st, A->d_wchunks, A->d_wblk, A->nwblk, A->d_wcounters, A->d_ai, A->d_aj, A->d_aa, x, yin, y);
-      return B200_OK;
-    }
-#define B200_MERGEX(MODE_)                                                                                   \
-    do {                                                                                                     \
-      if (A->nxtiles) B200_LAUNCH((k_mergex<MODE_, ADD>), A->nxtiles, MERGE_THREADS, 0, st, A->d_xtiles, A->d_ai, A->d_aj, A->d_aa, x, yin, y); \
-      if (A->nlong) B200_LAUNCH((k_longrow<MODE_, ADD>), (A->nlong + 3) / 4, 128, 0, st, A->nlong, A->d_longrows, A->d_ai, A->d_aj, A->d_aa, x, yin, y); \
-    } while (0)
-    if (mode == B200_MODE_EXACT_FMA) B200_MERGEX(B200_MODE_EXACT_FMA); else B200_MERGEX(B200_MODE_EXACT);
-#undef B200_MERGEX
+    // persistent warps: as many CTAs as fit (8 warps, 12-21 KB of shared memory each)
+    const int grid = std::max(1, std::min(sm_count() * 6, (A->nwblk + WM_WARPS - 1) / WM_WARPS));
+    if (mode == B200_MODE_EXACT_FMA)
+      B200_LAUNCH((k_wmerge<B200_MODE_EXACT_FMA, ADD>), grid, WM_WARPS * 32, 0, st, A->d_wchunks, A->d_wblk, A->nwblk, A->d_wcounters, A->d_ai, A->d_aj, A->d_aa, x, yin, y);
+    else
+      B200_LAUNCH((k_wmerge<B200_MODE_EXACT, ADD>), grid, WM_WARPS * 32, 0, st, A->d_wchunks, A->d_wblk, A->nwblk, A->d_wcounters, A->d_ai, A->d_aj, A->d_aa, x, yin, y);
     return B200_OK;
   }
   if (mode != B200_MODE_FAST && kernel == B200_KERNEL_VECTOR)

@@ -1,5 +1,5 @@
 """Power-law MatMult variants on one GPU: warp-granular exact-order kernel (k_wmerge) against the
-block-granular pair (k_mergex + k_longrow, B200_WMERGE=0), the split-row merge, and for the
+split-row merge (round 1's block-granular pair k_mergex + k_longrow, removed since, ran 1.01 ms), and for the
 transpose the stream kernel against k_wmerge.  Usage: python scripts/probe_powerlaw2.py [rows]"""
 import os, sys
 import numpy as np
@@ -38,9 +38,9 @@ def timed(tag, fn):
 
 
 timed("exact: k_wmerge (default)", lambda: A.mult(x, y, pk.MODE_EXACT))
-os.environ["B200_WMERGE"] = "0"
-timed("exact: k_mergex + k_longrow (B200_WMERGE=0)", lambda: A.mult(x, y, pk.MODE_EXACT))
-os.environ["B200_WMERGE"] = "1"
+os.environ["B200_MERGE_SPLIT"] = "1"
+timed("fast: split-row k_merge (B200_MERGE_SPLIT=1)", lambda: A.mult(x, y, pk.MODE_FAST))
+os.environ.pop("B200_MERGE_SPLIT")
 timed("exact_fma: k_wmerge", lambda: A.mult(x, y, pk.MODE_EXACT_FMA))
 yref = None
 A.build_transpose()
