@@ -187,6 +187,15 @@ extern "C" PetscErrorCode MatMultAdd_SeqAIJ(Mat A, Vec xx, Vec yy, Vec zz) { ret
 extern "C" PetscErrorCode MatMultTranspose_SeqAIJ(Mat A, Vec xx, Vec yy) { return seqaij_apply(A, 2, xx, NULL, yy); }
 extern "C" PetscErrorCode MatMultTransposeAdd_SeqAIJ(Mat A, Vec xx, Vec zz, Vec yy) { return seqaij_apply(A, 3, xx, zz, yy); }
 
+#ifndef B200_WITH_PETSC
+// The two functions below are compiled for the OFFLINE API slice only.  Against a real PETSc 3.7.6
+// tree (-DB200_WITH_PETSC) they must stay PETSc's own bodies -- MatDestroy_SeqAIJ also destroys the
+// row/col index sets, diag/imax/ilen/idiag/solve_work/saved_values, the inode data and the composed
+// functions; MatAssemblyEnd_SeqAIJ also sets rmax / the Info counters / the inode check -- with only
+// the residency hook lines added, exactly as the reference patches them
+// (src/openacc-step2/MatDestroy_SeqAIJ.patch, MatAssemblyEnd_SeqAIJ.patch; the hook lines are spelled
+// out in INTEGRATION.md section 3).  Defining look-alikes here would leak every SeqAIJ's private data.
+//
 // MatAssemblyEnd_SeqAIJ: PETSc 3.7.6 aij.c:973-1032 (scripts/petsc.sh:81).  The compaction below
 // follows the published algorithm (head visible at src/openacc-step2/
 // MatAssemblyEnd_SeqAIJ.patch:34-37: rows keep imax[i] reserved slots of which ilen[i] are used;
@@ -258,11 +267,10 @@ extern "C" PetscErrorCode MatDestroy_SeqAIJ(Mat A)
   int            rc = b200_petsc_release(&A->spptr);
   if (rc) return rc;
   ierr = MatSeqXAIJFreeAIJ(A, &a->a, &a->j, &a->i);CHKERRQ(ierr);
-#ifndef B200_WITH_PETSC
   free(a->diag); free(a->imax); free(a->ilen);
   free(a->compressedrow.i); free(a->compressedrow.rindex);
   free(a);
   A->data = NULL;
-#endif
   return 0;
 }
+#endif  // !B200_WITH_PETSC

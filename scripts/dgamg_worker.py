@@ -1,7 +1,7 @@
 """torchrun worker: CG + row-partitioned multigrid (petsc-openacc_b200/dgamg.py) on the reference
 problem, one rank per GPU.  Prints one JSON line on rank 0.
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 scripts/dgamg_worker.py 300
-NOT YET RUN (written after round 1's GPU budget was spent)."""
+Round 2: 200^3 on 2 GPUs and 300^3 on 8 GPUs (profiles/r02_dgamg_*.log)."""
 import json
 import os
 import sys
