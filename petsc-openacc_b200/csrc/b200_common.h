@@ -204,6 +204,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
   unsigned long long v;
@@ -262,11 +263,14 @@ __device__ __forceinline__ void halo_push_signal(const HaloArgs &h, int block)
   else __syncthreads();
   if (threadIdx.x == 0) {
     const int peer_slot = h.blocks[block].peer_slot;
-    __threadfence_system();
+    // release / acquire fences at system scope, not __threadfence_system(): that one is fence.sc and
+    // ptxas adds an invalidation of the whole L1 (CCTL.IVALL) to it, which the x gathers of the five
+    // CTAs on this SM then pay for
+    fence_acq_rel_sys();
     const unsigned prev = atomicAdd(h.done + peer_slot, 1u);
     if (prev == (unsigned)h.peers[peer_slot].nblocks - 1) {
       h.done[peer_slot] = 0;
-      __threadfence_system();
+      fence_acq_rel_sys();
       st_release_sys(h.peers[peer_slot].flag, h.seq);
     }
   }

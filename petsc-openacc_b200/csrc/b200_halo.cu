@@ -450,10 +450,10 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
       for (size_t c = 0; c < M->ridx.size(); ++c) rows[next[owner[c]]++] = (int)c;
       B200_TRY(up(&M->d_cta_ptr, ptr));
       B200_TRY(up(&M->d_cta_rows, rows));
-      if (lpt) {
-        B200_TRY(up(&M->d_sched_tiles, sched_tiles));
-        B200_TRY(up(&M->d_sched_first, first));
-      }
+      // the fused kernel always reads the CTA-major table (with B200_MPIAIJ_SCHED=0 it holds the
+      // round-robin assignment)
+      B200_TRY(up(&M->d_sched_tiles, sched_tiles));
+      B200_TRY(up(&M->d_sched_first, first));
       M->fused_grid = grid;
       M->fused_ok = true;
     }

@@ -272,12 +272,14 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
   const size_t   aabytes = (size_t)(cap + STREAM_PAD) * 8, ajbytes = stream_aj_bytes(cap, IDX8);
 
   const int tid = threadIdx.x;
-  // this CTA's tiles: every grid-th one, or its range of the launch's own schedule (HALO)
-  const bool sched = HALO && h.sched_first != nullptr;
-  if (sched) tiles = h.sched_tiles;
-  const int tile0 = sched ? __ldg(h.sched_first + bid) : bid;
-  const int tile1 = sched ? __ldg(h.sched_first + bid + 1) : ntiles;
-  const int tstep = sched ? 1 : nb;
+  // this CTA's tiles: every grid-th one, or (HALO, always) its range of the launch's own schedule --
+  // decided at compile time: the HALO instantiation sits at the register cap of 5 CTAs per SM, and
+  // two more live values in the tile loop made ptxas issue the eight gathers of a row in two groups
+  // of four (3 % slower)
+  if (HALO) tiles = h.sched_tiles;
+  const int tile0 = HALO ? __ldg(h.sched_first + bid) : bid;
+  const int tile1 = HALO ? __ldg(h.sched_first + bid + 1) : ntiles;
+  const int tstep = HALO ? 1 : nb;
   if (IDX8) {
     // all 256 table entries, also when the CTA has fewer than 256 threads (THREADS = 128 -> 160)
     for (int t = tid; t < 256; t += THREADS + 32) soffs[t] = __ldg(ix.offs + t);
@@ -349,9 +351,9 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
   pdl_wait();
   // VecScatterBegin: the stores go out now; the fence + flag release follow a tile or two later, when
   // the write acknowledgements are back and the fence is cheap (the peers need the flag at THEIR end)
-  const bool pusher = HALO && bid < h.npush;
-  if (pusher) halo_push_stores<THREADS>(h, x, bid);
-  const int signal_at = (tile1 - tile0 > tstep) ? 1 : 0;
+  if (HALO && bid < h.npush) halo_push_stores<THREADS>(h, x, bid);
+  // iteration after which a push CTA signals (-1: this CTA pushes nothing)
+  const int signal_at = (HALO && bid < h.npush) ? ((tile1 - tile0 > tstep) ? 1 : 0) : -1;
   double dacc = 0.0;
   int it = 0;
   for (int tile = tile0; tile < tile1; tile += tstep, ++it) {
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[s]);
-    if (pusher && it == signal_at) halo_push_signal<THREADS>(h, bid);
+    if (HALO && it == signal_at) halo_push_signal<THREADS>(h, bid);
   }
   if (HALO) {
     // one lane per source rank waits for that rank's flag; the consumer-only barrier publishes the
