@@ -7,10 +7,15 @@
  * timed CPU baseline.  The product (petsc-openacc_b200/) never links or calls it.
  *
  * PINNED: orc_matmult equals, bit for bit, the reference's own row loops compiled from its patch
- * files (oracle/_ref/libref_matmult.so: extract_ref_loops.py + ref_harness.c; tests/test_oracle.py),
+ * files (oracle/_ref/libref_matmult.so: extract_ref_loops.py + ref_harness.c; tests/test_oracle.py);
+ * orc_matmultadd, orc_matmulttranspose, orc_matmulttransposeadd and the compressed-row variants
+ * equal that same compiled loop run on equivalent matrices built independently with scipy -- A^T as
+ * CSR with ascending columns, [I | A] applied to [y; x], the non-empty rows scattered through rindex
+ * (tests/test_oracle.py::test_transpose_add_and_compressed_row_pinned_to_the_reference_loop);
  * and the generator below equals the reference's own src/helper.cpp compiled from where it lies
  * (oracle/_ref/libref_helper.so; tests/test_host_layer.py).
- * PARITY UNPINNED for everything else: the reference (olcf/PETSC-OpenACC) ships no golden
+ * PARITY UNPINNED for everything else (MPIAIJ set-up, DMDA grids, the multigrid, CG's reduction
+ * order): the reference (olcf/PETSC-OpenACC) ships no golden
  * vectors, no tests and no logs, and the rest of the arithmetic lives in PETSc 3.7.6
  * (petsc-lite-3.7.6.tar.gz, sha1 f2310cc0663848cbdcdf2ddf8ac48246a43d336b, scripts/petsc.sh:39,45)
  * which is downloaded at build time and is neither under /root/reference nor installable here (no
@@ -25,7 +30,8 @@
  *   - the reference's only known-answer test (analytic solution, src/main_ksp.cpp:5-15,120-121)
  *     is run against this generator in tests/test_oracle.py (test_known_answer_analytic_solution).
  * MatMultAdd / MatMultTranspose / compressed-row / MPIAIJ setup have NO text in the reference;
- * they restate PETSc 3.7.6's published algorithm from its documented behaviour ("[P376]" below).
+ * they restate PETSc 3.7.6's published algorithm from its documented behaviour ("[P376]" below);
+ * the first three are tied to the reference's MatMult loop as said above.
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: strict left-to-right, unfused).
  */
