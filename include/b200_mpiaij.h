@@ -103,6 +103,12 @@ int b200_mpiaij_check(b200_mpiaij_t M);
  * same error.  Host only, valid after every b200_mpiaij_set_peer_garray call.                     */
 int b200_mpiaij_pattern_symmetric(b200_mpiaij_t M, int32_t *first_unmatched_peer);
 
+/* The tile -> CTA schedule of the fused launch, host only (for tests): tiles that leave many ghost
+ * rows for the closing phase and the first `npush` CTAs (which also carry a push block) are charged
+ * extra tile times; everything else is dealt in index order to the least-loaded CTA.  cta_of[ntiles]. */
+int b200_mpiaij_tile_schedule(int32_t ntiles, const int32_t *ghost_rows_per_tile, int32_t grid,
+                              int32_t npush, double push_charge, int32_t *cta_of);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,6 +126,12 @@ int b200_sell_pack_size(int32_t m, const int32_t *h_ai, int32_t sigma, int32_t *
                         uint64_t *padded);
 int b200_sell_pack(int32_t m, const int32_t *h_ai, const int32_t *h_aj, const double *h_aa,
                    int32_t sigma, uint32_t *cs, int32_t *perm, double *val, int32_t *col);
+/* The plan of the warp-granular exact-order kernel (k_wmerge, skewed row lengths), host only:
+ * chunks4[4*c..] = {first row, rows (>= 0) | -2 first / -1 middle / -3 last piece of a row longer
+ * than 128 entries, first non-zero, last non-zero + 1}; blk[b], blk[b+1] = the chunks of work block b
+ * (a long row's pieces never straddle two blocks).  Sizes first, then the arrays.               */
+int b200_wmerge_plan_size(int32_t m, const int32_t *h_ai, int32_t *nchunks, int32_t *nblocks);
+int b200_wmerge_plan(int32_t m, const int32_t *h_ai, int32_t *chunks4, int32_t *blk);
 /* Device pointers of the mirrors (for tests / composition), any may be NULL.                 */
 int b200_csr_device_arrays(b200_csr_t A, const int32_t **d_ai, const int32_t **d_aj,
                            const double **d_aa);

@@ -80,6 +80,7 @@ ABI_SYMBOLS = [
     "b200_vec_pointwise_mult", "b200_vec_dot", "b200_vec_norm2", "b200_vec_norm_inf",
     "b200_vec_sum", "b200_cg_jacobi", "b200_gen_vector",
     "b200_csr_build_sell", "b200_sell_pack_size", "b200_sell_pack",
+    "b200_wmerge_plan_size", "b200_wmerge_plan",
 ]
 
 
@@ -249,6 +250,18 @@ def sell_pack(ai, aj, aa, sigma=1):
     return cs, perm[:nchunks.value * 32], val[:padded.value], col[:padded.value]
 
 
+def wmerge_plan(ai):
+    """Host-only plan of k_wmerge: (chunks[n, 4], blk[nblocks + 1])."""
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    m = len(ai) - 1
+    nc, nb = C.c_int32(0), C.c_int32(0)
+    check(lib.b200_wmerge_plan_size(C.c_int32(m), _np_ptr(ai), C.byref(nc), C.byref(nb)))
+    chunks = np.zeros((max(nc.value, 1), 4), np.int32)
+    blk = np.zeros(nb.value + 1, np.int32)
+    check(lib.b200_wmerge_plan(C.c_int32(m), _np_ptr(ai), _np_ptr(chunks), _np_ptr(blk)))
+    return chunks[:nc.value], blk
+
+
 def gen_vector(n, seed=0xB200):
     x = np.empty(n, dtype=np.float64)
     check(lib.b200_gen_vector(_np_ptr(x), C.c_int64(n), C.c_uint64(seed)))
@@ -322,7 +335,7 @@ MPIAIJ_SYMBOLS = [
     "b200_mpiaij_mult_end", "b200_mpiaij_mult", "b200_mpiaij_pack", "b200_mpiaij_mult_add_ghost",
     "b200_mpiaij_check", "b200_mpiaij_mult_host", "b200_mpiaij_mult_finish",
     "b200_mpiaij_set_rank_window", "b200_mpiaij_allreduce_sum", "b200_mpiaij_cg_jacobi",
-    "b200_mpiaij_pattern_symmetric",
+    "b200_mpiaij_pattern_symmetric", "b200_mpiaij_tile_schedule",
 ]
 ABI_SYMBOLS += MPIAIJ_SYMBOLS
 
@@ -442,6 +455,15 @@ class MpiAij:
         peer = C.c_int32(-1)
         rc = lib.b200_mpiaij_pattern_symmetric(self._h, C.byref(peer))
         return rc == 0, peer.value
+
+
+def mpiaij_tile_schedule(ghost_rows_per_tile, grid, npush=0, push_charge=6.0):
+    """Host-only tile -> CTA schedule of the fused MatMult_MPIAIJ launch."""
+    g = np.ascontiguousarray(ghost_rows_per_tile, dtype=np.int32)
+    out = np.zeros(max(len(g), 1), np.int32)
+    check(lib.b200_mpiaij_tile_schedule(C.c_int32(len(g)), _np_ptr(g), C.c_int32(grid), C.c_int32(npush),
+                                        C.c_double(push_charge), _np_ptr(out)))
+    return out[:len(g)]
 
 
 def gen_poisson7(M, size=1, rank=0, refpoint=True, vectors=False):

@@ -327,6 +327,51 @@ static int up(T **d, const std::vector<T> &h)
   return B200_OK;
 }
 
+// Tile -> CTA of the fused launch.  Round-robin keeps all CTAs sweeping the matrix in lockstep (the x
+// window they gather from stays in L2), but a face of the sub-box that is contiguous in memory puts
+// 256 ghost rows into every one of ~90 consecutive tiles, and a CTA that owns one of them would close
+// those rows on top of a full share of tiles and finish last; the first `npush` CTAs also carry a
+// push block (VecScatterBegin's stores and the fence behind them).  So: the push CTAs start with
+// `push_charge` tile times on their account (default 6.0: 8 GPUs, 32 push CTAs: 46.5 us per MatMult at
+// 4.0, 45.2 at 6.0; 16 CTAs / 8.0: 48.8; one block per SM / 1.0: 48.1 -- profiles/r02_halo_attribution.md;
+// never more than would leave them without a tile); the ghost-heavy tiles (>= 64 ghost rows) are dealt
+// out first, each charged 1 + ghost rows / 128 tile times (256 ghost rows ~ two tiles, measured with
+// scripts/probe_fused2.py); then the other tiles go, IN INDEX ORDER, to the CTA with the least load so
+// far -- round-robin again, except that a CTA holding a heavy tile or a push block sits out as many
+// rounds as it was charged.  Tiny matrices, where the charges would leave a CTA without any tile
+// (every CTA of the launch must own one), and lpt = false fall back to tile t on CTA t % grid.
+static void halo_tile_schedule(int ntiles, const int *gcount, int grid, int npush, double push_charge, bool lpt, int *cta_of)
+{
+  if (lpt && grid > 0) {
+    using Load = std::pair<double, int>;
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    const double charge = std::min(push_charge, std::max(0.0, (double)(ntiles / grid) - 1.0));
+    for (int b = 0; b < grid; ++b) heap.push({b < npush ? charge : 0.0, b});
+    std::vector<int> count((size_t)grid, 0);
+    auto deal = [&](int t) {
+      Load top = heap.top();
+      heap.pop();
+      cta_of[t] = top.second;
+      count[top.second]++;
+      heap.push({top.first + 1.0 + gcount[t] / 128.0, top.second});
+    };
+    for (int t = 0; t < ntiles; ++t) if (gcount[t] >= 64) deal(t);
+    for (int t = 0; t < ntiles; ++t) if (gcount[t] < 64) deal(t);
+    bool starved = false;
+    for (int b = 0; b < grid && b < ntiles; ++b) starved = starved || count[b] == 0;
+    if (!starved) return;
+  }
+  for (int t = 0; t < ntiles; ++t) cta_of[t] = grid > 0 ? t % grid : 0;
+}
+// host only: the schedule for the CPU tests
+extern "C" int b200_mpiaij_tile_schedule(int32_t ntiles, const int32_t *ghost_rows_per_tile, int32_t grid, int32_t npush,
+                                         double push_charge, int32_t *cta_of)
+{
+  if (ntiles < 0 || grid < 1 || (ntiles && (!ghost_rows_per_tile || !cta_of))) return set_error(B200_ERR_ARG, "b200_mpiaij_tile_schedule: bad argument");
+  halo_tile_schedule(ntiles, ghost_rows_per_tile, grid, npush, push_charge, true, cta_of);
+  return B200_OK;
+}
+
 // Elements per push block of the fused launch.  Measured on 8 B200s (profiles/r02_halo_attribution.md):
 // with one push block on every SM the stores to peer memory and the system-scope fences behind them
 // cost the launch 7 us of its 48; concentrated on a few CTAs -- which the tile schedule then gives
@@ -387,39 +432,11 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
           gcount[t]++;
         }
       }
-      // Tile -> CTA.  Round-robin keeps all CTAs sweeping the matrix in lockstep (the x window they
-      // gather from stays in L2), but a face of the sub-box that is contiguous in memory puts 256 ghost
-      // rows into every one of ~90 consecutive tiles, and a CTA that owns one of them would close
-      // those rows on top of a full share of tiles and finish last.  So: the ghost-heavy tiles are
-      // dealt out first, each charged 1 + ghost rows / 128 tile times (256 ghost rows ~ two tiles,
-      // measured with scripts/probe_fused2.py); then the other tiles go, IN INDEX ORDER, to the CTA with
-      // the least load so far -- round-robin again, except that a CTA holding a heavy tile sits out
-      // as many rounds as it was charged.  Each CTA's tiles stay in ascending order.
-      // B200_MPIAIJ_SCHED=0 keeps tile t on CTA t % grid.
+      // tile -> CTA (halo_tile_schedule), then the CTA-major copy of the tile table
       std::vector<int> cta_of((size_t)ntiles);
       const bool lpt = env_int("B200_MPIAIJ_SCHED", 1) != 0;
-      if (lpt) {
-        using Load = std::pair<double, int>;
-        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-        // the first CTAs also carry a push block (send lists as known now): VecScatterBegin's stores and
-        // the fence behind them are charged like B200_MPIAIJ_PUSH_CHARGE_TENTHS / 10 tiles (default 6.0:
-        // 8 GPUs, 32 push CTAs: 46.5 us per MatMult at 4.0, 45.2 at 6.0; 16 CTAs / 8.0: 48.8; one block per
-        // SM / 1.0: 48.1 -- profiles/r02_halo_attribution.md)
-        const int    npush = std::min(grid, fused_push_blocks(M, grid));
-        // (never more than would leave a push CTA without a tile of its own)
-        const double push_charge = std::min(env_int("B200_MPIAIJ_PUSH_CHARGE_TENTHS", 60) / 10.0, std::max(0.0, (double)(ntiles / grid) - 1.0));
-        for (int b = 0; b < grid; ++b) heap.push({b < npush ? push_charge : 0.0, b});
-        auto deal = [&](int t) {
-          Load top = heap.top();
-          heap.pop();
-          cta_of[t] = top.second;
-          heap.push({top.first + 1.0 + gcount[t] / 128.0, top.second});
-        };
-        for (int t = 0; t < ntiles; ++t) if (gcount[t] >= 64) deal(t);
-        for (int t = 0; t < ntiles; ++t) if (gcount[t] < 64) deal(t);
-      } else {
-        for (int t = 0; t < ntiles; ++t) cta_of[t] = t % grid;
-      }
+      halo_tile_schedule(ntiles, gcount.data(), grid, lpt ? std::min(grid, fused_push_blocks(M, grid)) : 0,
+                         env_int("B200_MPIAIJ_PUSH_CHARGE_TENTHS", 60) / 10.0, lpt, cta_of.data());
       std::vector<int>  first((size_t)grid + 1, 0);
       std::vector<int4> sched_tiles((size_t)ntiles);
       for (int t = 0; t < ntiles; ++t) first[cta_of[t] + 1]++;
@@ -427,18 +444,6 @@ extern "C" int b200_mpiaij_upload(b200_mpiaij_t M)
       {
         std::vector<int> next(first.begin(), first.end() - 1);
         for (int t = 0; t < ntiles; ++t) sched_tiles[next[cta_of[t]]++] = tiles[t];   // ascending inside a CTA
-      }
-      bool starved = false;
-      for (int b = 0; b < grid; ++b) starved = starved || first[b + 1] == first[b];
-      if (starved) {
-        // (tiny matrices: the charges can leave a CTA without a tile; every CTA of the launch must
-        // own at least one) -- plain round-robin
-        for (int t = 0; t < ntiles; ++t) cta_of[t] = t % grid;
-        std::fill(first.begin(), first.end(), 0);
-        for (int t = 0; t < ntiles; ++t) first[cta_of[t] + 1]++;
-        for (int b = 0; b < grid; ++b) first[b + 1] += first[b];
-        std::vector<int> next(first.begin(), first.end() - 1);
-        for (int t = 0; t < ntiles; ++t) sched_tiles[next[cta_of[t]]++] = tiles[t];
       }
       std::vector<int> owner(M->ridx.size()), ptr((size_t)grid + 1, 0), rows(M->ridx.size());
       for (size_t c = 0; c < M->ridx.size(); ++c) {

@@ -1018,12 +1018,10 @@ static int build_idx8(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
 // at most WM_CAP rows: runs of empty rows); a row longer than WM_CAP becomes pieces of WM_CAP.  A work
 // block is ~WM_BLOCK consecutive chunks and never separates the pieces of one row.
 #define WM_BLOCK 16
-static int build_wmerge_plan(b200_csr_s *A, const int32_t *ai)
+static void wmerge_plan(int m, const int32_t *ai, std::vector<int4> &chunks, std::vector<int> &blk)
 {
-  const int m = A->m;
-  std::vector<int4> chunks;
-  std::vector<int>  blk;
-  chunks.reserve((size_t)A->nz / (WM_CAP / 2) + 16);
+  chunks.clear(); blk.clear();
+  chunks.reserve((size_t)ai[m] / (WM_CAP / 2) + 16);
   int r = 0;
   while (r < m) {
     const int len = ai[r + 1] - ai[r];
@@ -1047,6 +1045,35 @@ static int build_wmerge_plan(b200_csr_s *A, const int32_t *ai)
     blk.push_back((int)e);
     c = e;
   }
+}
+
+// the plan itself, host only (no device needed): for the CPU tests, which walk it the way the kernel does
+extern "C" int b200_wmerge_plan_size(int32_t m, const int32_t *h_ai, int32_t *nchunks, int32_t *nblocks)
+{
+  if (m < 0 || !h_ai || !nchunks || !nblocks) return set_error(B200_ERR_ARG, "b200_wmerge_plan_size: bad argument");
+  std::vector<int4> chunks;
+  std::vector<int>  blk;
+  wmerge_plan(m, h_ai, chunks, blk);
+  *nchunks = (int32_t)chunks.size();
+  *nblocks = (int32_t)blk.size() - 1;
+  return B200_OK;
+}
+extern "C" int b200_wmerge_plan(int32_t m, const int32_t *h_ai, int32_t *chunks4, int32_t *blk)
+{
+  if (m < 0 || !h_ai || !chunks4 || !blk) return set_error(B200_ERR_ARG, "b200_wmerge_plan: bad argument");
+  std::vector<int4> chunks;
+  std::vector<int>  b;
+  wmerge_plan(m, h_ai, chunks, b);
+  for (size_t c = 0; c < chunks.size(); ++c) { chunks4[4 * c] = chunks[c].x; chunks4[4 * c + 1] = chunks[c].y; chunks4[4 * c + 2] = chunks[c].z; chunks4[4 * c + 3] = chunks[c].w; }
+  std::copy(b.begin(), b.end(), blk);
+  return B200_OK;
+}
+
+static int build_wmerge_plan(b200_csr_s *A, const int32_t *ai)
+{
+  std::vector<int4> chunks;
+  std::vector<int>  blk;
+  wmerge_plan(A->m, ai, chunks, blk);
   A->nwchunks = (int)chunks.size();
   A->nwblk    = (int)blk.size() - 1;
   B200_TRY(dev_alloc(&A->d_wchunks, chunks.size(), A));

@@ -141,3 +141,36 @@ def test_unsymmetric_communication_pattern_is_reported(pk):
                     a.set_peer_garray(b.rank, b.garray())
         assert all(m.pattern_symmetric()[0] for m in ms)
         [m.destroy() for m in ms]
+
+
+def test_fused_launch_tile_schedule(pk):
+    """Tile -> CTA of the fused MatMult_MPIAIJ launch: every tile exactly once, every CTA at least one,
+    plain round-robin when nothing is charged, fewer tiles for the CTAs that close a ghost-heavy tile or
+    carry a push block, and the light tiles still dealt in index order (lockstep sweep)."""
+    grid = 740
+    none = np.zeros(13184, np.int32)
+    assert np.array_equal(pk.mpiaij_tile_schedule(none, grid), np.arange(13184) % grid)
+    # rank 0 of the 8-rank 300^3 decomposition: the last 88 tiles are a contiguous face (256 ghost rows each),
+    # a y-face tile every 88 tiles, x-face rows everywhere
+    g = np.full(13184, 2, np.int32)
+    g[::88] = 150
+    g[-88:] = 256
+    cta = pk.mpiaij_tile_schedule(g, grid, npush=32, push_charge=6.0)
+    assert cta.min() == 0 and cta.max() == grid - 1
+    count = np.bincount(cta, minlength=grid)
+    assert count.min() >= 1 and count.sum() == len(g)
+    load = np.bincount(cta, weights=1.0 + g / 128.0, minlength=grid)
+    load[:32] += 6.0
+    assert load.max() - load.min() <= 2.2                       # balanced to within one tile + its charge
+    assert count[:32].max() <= count[32:].max() - 5                # the push CTAs stream ~6 tiles less
+    heavy_owner = cta[-88:]
+    assert len(set(heavy_owner)) == 88                           # one ghost face tile per CTA at most
+    assert count[heavy_owner].max() <= count.max() - 2           # and those CTAs sit out ~3 rounds
+    # lockstep: the light tiles of a CTA are spread over the whole matrix, like round-robin's
+    light = np.nonzero(g < 64)[0]
+    for b in (40, 400, 739):
+        mine = light[cta[light] == b]
+        assert np.all(np.diff(mine) > 0) and np.diff(mine).max() < 3 * grid
+    # tiny matrices: the charges must not starve a CTA
+    small = np.array([300, 0, 0, 0, 0, 0, 0], np.int32)
+    assert sorted(pk.mpiaij_tile_schedule(small, 7, npush=3, push_charge=6.0)) == list(range(7))
