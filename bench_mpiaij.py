@@ -110,13 +110,13 @@ def run(args, pk, B):
             sampler.start()
         ms = timed(mult_p2p, args.steps, warm)
         M.check()
-        launches = pk.launch_count() - l0
+        launches = (pk.launch_count() - l0) * args.steps // (args.steps + warm)     # of the timed region, this rank
         ms_nccl = timed(mult_nccl, max(5, args.steps // 4), 3)
     else:
         if rank == 0:
             sampler.start()
         ms = timed(mult_nccl, args.steps, warm)
-        launches = pk.launch_count() - l0
+        launches = (pk.launch_count() - l0) * args.steps // (args.steps + warm)
         ms_nccl = ms
     y_dev = y.cpu().numpy()
 
