@@ -214,6 +214,11 @@ __global__ void __launch_bounds__(256) k_vector(int m, const int *__restrict__ i
 struct Idx8Args {
   const unsigned char *aj8;   // nz (+ pad) codes
   const int           *offs;  // 256 entries: col = row + offs[code]
+  // RL8 (compressed row pointers, rows of at most 255 entries): one byte of row LENGTH per row and,
+  // per tile and warp, the offset of the warp's first row; the lanes rebuild their row's range with a
+  // warp scan.  1.125 instead of 4 bytes per row of DRAM traffic; same values, same order, same bits.
+  const unsigned char *rl8;   // m (+ pad) row lengths
+  const int           *wbase; // ntiles x (THREADS / 32): ai[first row of the warp]
 };
 
 __host__ __device__ inline size_t stream_aj_bytes(int cap, bool idx8)
@@ -236,7 +241,7 @@ __host__ __device__ inline size_t stream_header_bytes(bool idx8) { return idx8 ?
 //   4  y_i = t_i and the CTA accumulates x_i * t_i: CG's (p, A p) without a second pass over p and w
 enum { EPI_NONE = 0, EPI_ADD = 1, EPI_RESIDUAL = 2, EPI_JACOBI = 3, EPI_DOT = 4 };
 
-template <int MODE, int EPI, int THREADS, bool HALO, bool IDX8>
+template <int MODE, int EPI, int THREADS, bool HALO, bool IDX8, bool RL8 = false>
 __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     k_stream(const int4 *__restrict__ tiles_in, int ntiles, const int *__restrict__ ii,
              const int *__restrict__ aj, const double *__restrict__ aa,
@@ -321,13 +326,21 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
         const int      nn8 = ((d.w + 15) & ~15) - s16;   // IDX8: bytes of codes
         // expect exactly the bytes issued below: a tile of empty rows (nn == 0) copies no codes even
         // when the 16-byte rounding of the code range (nn8) is not empty
-        mbar_expect_tx(&full[s], (uint32_t)((nn > 0 ? nn * 8 + (IDX8 ? nn8 : nn * 4) : 0) + nr * 4));
+        const int      r16 = d.x & ~15;
+        const int      nrb = ((d.y + 15) & ~15) - r16;   // RL8: bytes of row lengths
+        mbar_expect_tx(&full[s], (uint32_t)((nn > 0 ? nn * 8 + (IDX8 ? nn8 : nn * 4) : 0) + (RL8 ? nrb + (THREADS / 32) * 4 : nr * 4)));
         if (nn > 0) {
           bulk_g2s(saa, aa + s4, (uint32_t)nn * 8, &full[s], pol);
           if (IDX8) bulk_g2s(saj, ix.aj8 + s16, (uint32_t)nn8, &full[s], pol);
           else bulk_g2s(saj, aj + s4, (uint32_t)nn * 4, &full[s], pol);
         }
-        bulk_g2s(sii, ii + r0a, (uint32_t)nr * 4, &full[s], pol);
+        if (RL8) {
+          // [0, 32): the warps' first offsets; [32, ...): the row lengths from the 16-byte boundary below d.x
+          bulk_g2s(sii, ix.wbase + (size_t)tile * (THREADS / 32), (uint32_t)(THREADS / 32) * 4, &full[s], pol);
+          bulk_g2s(reinterpret_cast<unsigned char *>(sii) + 32, ix.rl8 + r16, (uint32_t)nrb, &full[s], pol);
+        } else {
+          bulk_g2s(sii, ii + r0a, (uint32_t)nr * 4, &full[s], pol);
+        }
       }
     } else if (HALO) {
       // The other 31 lanes of the producer warp have nothing to do: they walk this CTA's ghost-row
@@ -370,8 +383,23 @@ __global__ void __launch_bounds__(THREADS + 32, THREADS == 256 ? 5 : 10)
     if (EPI == EPI_ADD) { if (r < d.y) sum = yin[r]; }
     if (EPI == EPI_RESIDUAL || EPI == EPI_JACOBI) { if (r < d.y) bi = yin[r]; }
     mbar_wait(&full[s], (it / stages) & 1);
+    int lo, hi;
+    if (RL8) {
+      const unsigned char *srl = reinterpret_cast<const unsigned char *>(sii - (d.x & 3)) + 32 + (d.x & 15);
+      const int len = (r < d.y) ? (int)srl[tid] : 0;
+      int incl = len;   // inclusive scan of the row lengths over the warp
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((tid & 31) >= off) incl += t;
+      }
+      hi = (sii - (d.x & 3))[tid >> 5] + incl;
+      lo = hi - len;
+    } else {
+      lo = sii[tid];
+      hi = sii[tid + 1];
+    }
     if (r < d.y) {
-      const int lo = sii[tid], hi = sii[tid + 1];
       const int p  = lo - (d.z & ~3);
       const int p8 = lo - (d.z & ~15);
       const int n  = hi - lo;
@@ -808,6 +836,10 @@ struct b200_csr_s {
   unsigned char *d_aj8 = nullptr;
   int           *d_offs = nullptr;
   int32_t        noffs = 0;
+  // compressed row pointers (see RL8)
+  bool           rl8 = false;
+  unsigned char *d_rl8 = nullptr;
+  int           *d_wbase = nullptr;
   std::vector<int4> h_tiles;
   int32_t ntiles = 0, stream_threads = 256, stream_cap = 0, stream_stages = 0, stream_grid = 0;
   size_t  stream_smem = 0;
@@ -883,6 +915,11 @@ static int stream_set_attr(size_t smem)
   B200_SET(EPI_NONE, true, false);      B200_SET(EPI_NONE, true, true);
   B200_SET(EPI_DOT, true, false);       B200_SET(EPI_DOT, true, true);
 #undef B200_SET
+#define B200_SET_RL8(EPI_)                                                                          \
+  B200_CUDA_TRY(cudaFuncSetAttribute(k_stream<MODE, EPI_, THREADS, false, true, true>,               \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+  B200_SET_RL8(EPI_NONE); B200_SET_RL8(EPI_ADD); B200_SET_RL8(EPI_RESIDUAL); B200_SET_RL8(EPI_JACOBI); B200_SET_RL8(EPI_DOT);
+#undef B200_SET_RL8
   return B200_OK;
 }
 
@@ -1184,6 +1221,20 @@ static int build_plan(b200_csr_s *A, const int32_t *ai, const int32_t *aj)
       A->stream_stages  = stages;
       B200_TRY(dev_alloc(&A->d_tiles, tiles.size(), A));
       B200_CUDA_TRY(cudaMemcpy(A->d_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+      if (i8 && A->rmax <= 255 && env_int("B200_ROWLEN8", 1)) {
+        // one-byte row lengths + the first offset of every warp of every tile (see RL8 at k_stream)
+        std::vector<unsigned char> rl((size_t)m + 64, 0);
+        for (int i = 0; i < m; ++i) rl[i] = (unsigned char)(ai[i + 1] - ai[i]);
+        const int wpt = threads / 32;
+        std::vector<int> wb(tiles.size() * (size_t)wpt);
+        for (size_t t = 0; t < tiles.size(); ++t)
+          for (int w = 0; w < wpt; ++w) wb[t * wpt + w] = ai[std::min(tiles[t].x + 32 * w, tiles[t].y)];
+        B200_TRY(dev_alloc(&A->d_rl8, rl.size(), A));
+        B200_TRY(dev_alloc(&A->d_wbase, wb.size(), A));
+        B200_CUDA_TRY(cudaMemcpy(A->d_rl8, rl.data(), rl.size(), cudaMemcpyHostToDevice));
+        B200_CUDA_TRY(cudaMemcpy(A->d_wbase, wb.data(), wb.size() * sizeof(int), cudaMemcpyHostToDevice));
+        A->rl8 = true;
+      }
       B200_TRY(stream_set_all_attrs(threads, A->stream_smem));
       int ctas = 0;
       if (threads == 256) B200_TRY(stream_occupancy<256>(A->stream_smem, &ctas));
@@ -1384,7 +1435,7 @@ extern "C" int b200_csr_destroy(b200_csr_t A)
   if (A->T) b200_csr_destroy(A->T);
   cudaFree(A->d_ai); cudaFree(A->d_aj); cudaFree(A->d_aa);
   cudaFree(A->d_cpi); cudaFree(A->d_ridx); cudaFree(A->d_tiles);
-  cudaFree(A->d_aj8); cudaFree(A->d_offs);
+  cudaFree(A->d_aj8); cudaFree(A->d_offs); cudaFree(A->d_rl8); cudaFree(A->d_wbase);
   cudaFree(A->d_mtiles); cudaFree(A->d_msplit); cudaFree(A->d_mhead); cudaFree(A->d_mtail);
   cudaFree(A->d_wchunks); cudaFree(A->d_wblk); cudaFree(A->d_wcounters);
   sell_drop(A);
@@ -1450,12 +1501,22 @@ static int launch_stream_any(b200_csr_s *A, int grid, const int4 *tiles, int nti
                              const double *yin, double *y, const HaloArgs &h, cudaStream_t st,
                              const double *aux = nullptr, const DotArgs &dot = DotArgs{})
 {
-  const Idx8Args ix{A->d_aj8, A->d_offs};
+  const Idx8Args ix{A->d_aj8, A->d_offs, A->d_rl8, A->d_wbase};
   B200_TRY(stream_set_all_attrs(0, 0));   // first use on this device (a handle made on another one)
 #define B200_STREAM_GO(T, I8)                                                                       \
   B200_LAUNCH_PDL((k_stream<MODE, EPI, T, HALO, I8>), grid, T + 32, A->stream_smem, st, tiles, ntiles, \
                   (const int *)A->d_ai, (const int *)A->d_aj, (const double *)A->d_aa, x, yin, y,     \
                   (int)A->stream_cap, (int)A->stream_stages, h, ix, aux, dot)
+  // one-byte row lengths: whole-matrix launches of the byte-code plan (the tile index addresses wbase)
+  if (!HALO && A->rl8 && tiles == A->d_tiles) {
+#define B200_STREAM_GO_RL8(T)                                                                       \
+  B200_LAUNCH_PDL((k_stream<MODE, EPI, T, false, true, true>), grid, T + 32, A->stream_smem, st, tiles, ntiles, \
+                  (const int *)A->d_ai, (const int *)A->d_aj, (const double *)A->d_aa, x, yin, y,     \
+                  (int)A->stream_cap, (int)A->stream_stages, h, ix, aux, dot)
+    if (A->stream_threads == 256) B200_STREAM_GO_RL8(256); else B200_STREAM_GO_RL8(128);
+#undef B200_STREAM_GO_RL8
+    return B200_OK;
+  }
   if (A->idx8) { if (A->stream_threads == 256) B200_STREAM_GO(256, true); else B200_STREAM_GO(128, true); }
   else { if (A->stream_threads == 256) B200_STREAM_GO(256, false); else B200_STREAM_GO(128, false); }
 #undef B200_STREAM_GO
