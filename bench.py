@@ -389,7 +389,7 @@ def run_ours(args):
     kname = pk.KERNEL_NAMES[info.kernel_fast if mode == pk.MODE_FAST else info.kernel_exact]
     if kname == "merge":
         kname = "wmerge"
-    stream_bytes = nnz * (9 if info.index8_diagonals else 12) + m * 20
+    stream_bytes = nnz * (9 if info.index8_diagonals else 12) + m * 16 + int(m * (1.125 if info.rowlen8 else 4))
     roof = {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": peak, "unit": "GB/s",
             "frac": nbytes / ms / 1e6 / peak,
             "traffic": ncu_traffic() if args.workload == "matmult" else ncu_traffic(f"dram_bytes_per_launch_{args.workload}"),
@@ -399,9 +399,9 @@ def run_ours(args):
             "dram_bytes_streamed_model": stream_bytes,
             "dram_gbs_streamed_model": stream_bytes / ms / 1e6,
             "note": ("achieved = ALGORITHMIC bytes (nnz*12 + rows*20) / average launch duration over the timed region. The "
-                     "default plan streams 1-byte diagonal codes instead of 4-byte column indices (lossless, bit-exact), so "
-                     "real DRAM traffic is nnz*9 + rows*20 and frac can exceed 1; 'int32_index' is the same MatMult without "
-                     "that compression.") if info.index8_diagonals else
+                     "default plan streams 1-byte diagonal codes instead of 4-byte column indices and 1-byte row lengths instead "
+                     "of 4-byte row pointers (lossless, bit-exact), so real DRAM traffic is nnz*9 + rows*17.1 and frac can exceed "
+                     "1; 'int32_index' is the same MatMult without that compression.") if info.index8_diagonals else
                     "achieved = algorithmic bytes (nnz*12 + rows*20) / average launch duration over the timed region"}
     if plain:
         roof["int32_index"] = dict(plain, frac=plain["value"] / peak)
@@ -422,7 +422,7 @@ def run_ours(args):
         "gflops": 2.0 * nnz / ms / 1e6,
         "config": workload_config(args, m, nnz),
         "plan": {"mode": args.mode, "kernel": f"k_{kname}", "index8_diagonals": int(info.index8_diagonals),
-                 "parity_vs_oracle": parity, "pdl": os.environ.get("B200_PDL", "1") != "0"},
+                 "rowlen8": int(info.rowlen8), "parity_vs_oracle": parity, "pdl": os.environ.get("B200_PDL", "1") != "0"},
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": nbytes / e2e_ms / 1e6, "unit": "GB/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": m * 8, "d2h_bytes_per_step": m * 8, "steps": e2e_steps,

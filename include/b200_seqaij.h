@@ -85,6 +85,8 @@ typedef struct {
   int32_t sell_chunks;       /* > 0: a SELL-32-sigma copy is resident (chunks of 32 rows)          */
   int32_t sell_sigma;        /* its sorting window                                               */
   uint64_t sell_padded_nnz;  /* entries it stores, padding included                              */
+  int32_t rowlen8;           /* 1: the stream plan reads 1-byte row lengths instead of 4-byte row pointers */
+  int32_t reserved;
 } b200_csr_info_t;
 
 /* ---- runtime ------------------------------------------------------------------------------ */

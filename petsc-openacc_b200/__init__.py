@@ -56,7 +56,8 @@ class CsrInfo(C.Structure):
                 ("merge_tiles", C.c_int32), ("has_transpose", C.c_int32),
                 ("index8_diagonals", C.c_int32),
                 ("hist", C.c_int32 * 16), ("device_bytes", C.c_uint64),
-                ("sell_chunks", C.c_int32), ("sell_sigma", C.c_int32), ("sell_padded_nnz", C.c_uint64)]
+                ("sell_chunks", C.c_int32), ("sell_sigma", C.c_int32), ("sell_padded_nnz", C.c_uint64),
+                ("rowlen8", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CgResult(C.Structure):

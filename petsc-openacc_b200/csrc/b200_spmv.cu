@@ -1462,6 +1462,7 @@ extern "C" int b200_csr_get_info(b200_csr_t A, b200_csr_info_t *info)
   memcpy(info->hist, A->hist, sizeof A->hist);
   info->device_bytes = A->device_bytes + (A->T ? A->T->device_bytes : 0);
   info->sell_chunks = A->sell_chunks; info->sell_sigma = A->sell_sigma; info->sell_padded_nnz = A->sell_padded;
+  info->rowlen8 = A->rl8 ? 1 : 0;
   return B200_OK;
 }
 
