@@ -859,6 +859,9 @@ struct b200_csr_s {
   unsigned int  *d_scs = nullptr;
   int32_t        sell_chunks = 0, sell_sigma = 0;
   uint64_t       sell_padded = 0;
+  // column blocks of the k_wmerge plan when x does not fit L2 (see build_colblocks): A = [A_0 | A_1 | ...]
+  std::vector<b200_csr_s *> colblocks;
+  bool is_colblock = false;
   // vector plan
   int32_t vector_lanes = 8;
   int32_t kernel_fast = B200_KERNEL_ROW, kernel_exact = B200_KERNEL_ROW, kernel_override = 0;
@@ -1329,9 +1332,64 @@ static void build_host_blocks(b200_csr_s *A, const int32_t *ai, const int32_t *a
   }
 }
 
-static int create_common(b200_csr_s *A, const int32_t *h_ai, const int32_t *h_aj)
+// Column blocks for skewed matrices whose x does not stay in L2.  The gathers of k_wmerge are what
+// bounds it, and they run 20 % faster when x is L2 resident (10 M rows, 98 M non-zeros: 0.686 ms with
+// a 40 MB x, 0.860 ms with 80 MB; profiles/r02_powerlaw.md) -- the 126 MB L2 keeps ~60 MB of a randomly
+// gathered vector under the matrix stream.  So A is cut into column blocks [A_0 | A_1 | ...] of at
+// most B200_COLBLOCK_MB (default 40) of x each, every block a CSR of its own with its own k_wmerge
+// plan, and y = A x becomes y = A_0 x, y += A_1 x, ... -- MatMultAdd continues the row sum from y, and
+// because columns ascend inside a row that is exactly the reference's left-to-right order: same bits.
+// An extra copy of aj/aa (like the explicit transpose); dropped by b200_csr_update_values.
+static int alloc_mirrors(b200_csr_s *A);
+static int fill_ai_tail(b200_csr_s *A);
+static int build_colblocks(b200_csr_s *A, const int32_t *ai, const int32_t *aj, const double *aa)
 {
-  return build_plan(A, h_ai, h_aj);
+  if (A->is_colblock || !aa || !aj || !env_int("B200_COLBLOCK", 1)) return B200_OK;
+  // (B200_COLBLOCK_KB: the same limit in KB, so that the tests can block small matrices)
+  const int    kb    = env_int("B200_COLBLOCK_KB", 0);
+  const size_t limit = kb > 0 ? (size_t)kb << 10 : (size_t)std::max(1, env_int("B200_COLBLOCK_MB", 40)) << 20;
+  const size_t xbytes = (size_t)A->n * sizeof(double);
+  if (xbytes <= limit + limit / 2) return B200_OK;                  // up to 60 MB the one-pass kernel is as fast
+  const int nb = (int)((xbytes + limit - 1) / limit);
+  const int m = A->m;
+  std::vector<int32_t> bi((size_t)m + 1), bj;
+  std::vector<double>  ba;
+  std::vector<int32_t> from(ai, ai + m);                            // next unread entry of every row
+  for (int b = 0; b < nb; ++b) {
+    const int32_t cend = (b + 1 == nb) ? A->n : (int32_t)((long long)A->n * (b + 1) / nb);
+    bj.clear(); ba.clear();
+    bi[0] = 0;
+    for (int r = 0; r < m; ++r) {
+      int32_t k = from[r];
+      while (k < ai[r + 1] && aj[k] < cend) { bj.push_back(aj[k]); ba.push_back(aa[k]); ++k; }
+      from[r] = k;
+      bi[r + 1] = (int32_t)bj.size();
+    }
+    b200_csr_s *S = new (std::nothrow) b200_csr_s;
+    if (!S) return set_error(B200_ERR_MEM, "out of host memory");
+    S->m = m; S->n = A->n; S->nz = bi[m]; S->is_colblock = true;
+    A->colblocks.push_back(S);                                      // owned from here on (destroyed with A)
+    B200_TRY(alloc_mirrors(S));
+    B200_CUDA_TRY(cudaMemcpy(S->d_ai, bi.data(), ((size_t)m + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    B200_TRY(fill_ai_tail(S));
+    if (S->nz) {
+      B200_CUDA_TRY(cudaMemcpy(S->d_aj, bj.data(), (size_t)S->nz * sizeof(int), cudaMemcpyHostToDevice));
+      B200_CUDA_TRY(cudaMemcpy(S->d_aa, ba.data(), (size_t)S->nz * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // the block runs k_wmerge whatever its own histogram says (half of its rows may be empty)
+    S->rmax = A->rmax;
+    B200_TRY(build_wmerge_plan(S, bi.data()));
+    S->kernel_fast = S->kernel_exact = B200_KERNEL_MERGE;
+    A->device_bytes += S->device_bytes;
+  }
+  return B200_OK;
+}
+
+static int create_common(b200_csr_s *A, const int32_t *h_ai, const int32_t *h_aj, const double *h_aa = nullptr)
+{
+  B200_TRY(build_plan(A, h_ai, h_aj));
+  if (A->kernel_exact == B200_KERNEL_MERGE && A->nwblk) B200_TRY(build_colblocks(A, h_ai, h_aj, h_aa));
+  return B200_OK;
 }
 
 extern "C" int b200_init(int device)
@@ -1390,7 +1448,7 @@ extern "C" int b200_csr_create(b200_csr_t *out, int32_t m, int32_t n, const int3
       B200_CUDA_TRY(cudaMemcpy(A->d_aj, h_aj, (size_t)nz * sizeof(int), cudaMemcpyHostToDevice));
       B200_CUDA_TRY(cudaMemcpy(A->d_aa, h_aa, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice));
     }
-    B200_TRY(create_common(A, h_ai, h_aj));
+    B200_TRY(create_common(A, h_ai, h_aj, h_aa));
     if (A->ntiles) build_host_blocks(A, h_ai, h_aj, A->h_tiles);
     return B200_OK;
   }();
@@ -1445,6 +1503,8 @@ extern "C" int b200_csr_update_values(b200_csr_t A, const double *h_aa)
   if (!A || (!h_aa && A->nz)) return set_error(B200_ERR_ARG, "b200_csr_update_values: bad argument");
   if (A->nz) B200_CUDA_TRY(cudaMemcpy(A->d_aa, h_aa, (size_t)A->nz * sizeof(double), cudaMemcpyHostToDevice));
   if (A->T) { b200_csr_destroy(A->T); A->T = nullptr; }  // stale transpose values
+  for (auto *b : A->colblocks) b200_csr_destroy(b);       // stale column-block copies: back to the one-pass kernel
+  A->colblocks.clear();
   if (A->sell_chunks) {                                  // stale SELL values: back to the plan's kernel
     sell_drop(A);
     if (A->kernel_override == B200_KERNEL_SELL) A->kernel_override = 0;
@@ -1456,6 +1516,7 @@ extern "C" int b200_csr_destroy(b200_csr_t A)
 {
   if (!A) return B200_OK;
   if (A->T) b200_csr_destroy(A->T);
+  for (auto *b : A->colblocks) b200_csr_destroy(b);
   cudaFree(A->d_ai); cudaFree(A->d_aj); cudaFree(A->d_aa);
   cudaFree(A->d_cpi); cudaFree(A->d_ridx); cudaFree(A->d_tiles);
   cudaFree(A->d_aj8); cudaFree(A->d_offs); cudaFree(A->d_rl8); cudaFree(A->d_wbase);
@@ -1808,6 +1869,14 @@ static int spmv_dispatch(b200_csr_s *A, const double *x, const double *yin, doub
   const bool have_exact_plan = A->nwblk > 0;
   if (kernel == B200_KERNEL_MERGE && (mode != B200_MODE_FAST || (have_exact_plan && !env_int("B200_MERGE_SPLIT", 0)))) {
     if (!have_exact_plan) return set_error(B200_ERR_ARG, "no exact-order merge plan for this matrix");
+    if (!A->colblocks.empty()) {
+      // y = A_0 x, then y += A_b x block after block: the row sums continue left to right (build_colblocks)
+      for (size_t b = 0; b < A->colblocks.size(); ++b) {
+        if (b == 0) B200_TRY(spmv_dispatch<ADD>(A->colblocks[0], x, yin, y, mode, st));
+        else B200_TRY(spmv_dispatch<true>(A->colblocks[b], x, y, y, mode, st));
+      }
+      return B200_OK;
+    }
     // persistent warps: as many CTAs as fit (8 warps, 12-21 KB of shared memory each)
     const int grid = std::max(1, std::min(sm_count() * 6, (A->nwblk + WM_WARPS - 1) / WM_WARPS));
     if (mode == B200_MODE_EXACT_FMA)

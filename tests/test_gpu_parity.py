@@ -340,6 +340,35 @@ def test_tiles_of_empty_rows_with_unaligned_code_offset(pk, cuda, monkeypatch, t
     A.destroy()
 
 
+@pytest.mark.parametrize("name", ["powerlaw_20k", "long_rows", "random_ragged"])
+def test_column_blocks_of_the_skewed_plan_keep_the_bits(pk, cuda, monkeypatch, name):
+    """When x does not fit L2 the k_wmerge plan is cut into column blocks, y = A_0 x, y += A_1 x, ...;
+    columns ascend inside a row, so that is still the reference's left-to-right sum.  Forced here on
+    small matrices (B200_COLBLOCK_KB); the 10 M-row matrix of test_gpu_fullsize takes it by itself."""
+    ai, aj, aa, n = CASES[name]
+    m = len(ai) - 1
+    monkeypatch.setenv("B200_COLBLOCK_KB", "16")
+    A = pk.Csr(ai, aj, aa, n=n)
+    monkeypatch.delenv("B200_COLBLOCK_KB")
+    info = A.info()
+    x, y0 = gen.uniform_pm1(n, 21), gen.uniform_pm1(m, 22)
+    if pk.KERNEL_NAMES[info.kernel_exact] != "merge":
+        A.set_kernel(pk.KERNEL_MERGE)       # (a plan that is not skewed enough: no blocks, plain k_wmerge)
+    for mode, fma in ((pk.MODE_EXACT, False), (pk.MODE_EXACT_FMA, True), (pk.MODE_FAST, None)):
+        y = _run(pk, cuda, A, x, mode)
+        if fma is None:
+            ref = oracle.matmult(ai, aj, aa, x)
+            assert np.all(np.abs(y - ref) <= TOL * oracle.row_abs_sum(ai, aj, aa, x))
+        else:
+            assert np.array_equal(y, oracle.matmult(ai, aj, aa, x, fma=fma)), (name, mode)
+            assert np.array_equal(_run(pk, cuda, A, x, mode, add=y0), oracle.matmultadd(ai, aj, aa, x, y0, fma=fma)), (name, mode)
+    if pk.KERNEL_NAMES[info.kernel_exact] == "merge":
+        assert info.device_bytes > 1.8 * (len(aj) * 12)          # the blocks are a second copy of aj / aa
+    A.update_values(aa * 0.5)                                  # drops the blocks, same plan without them
+    assert np.array_equal(_run(pk, cuda, A, x, pk.MODE_EXACT), oracle.matmult(ai, aj, aa * 0.5, x))
+    A.destroy()
+
+
 def test_compressed_index_plan_and_equivalence(pk, cuda, monkeypatch):
     """Stencil matrices stream 1-byte diagonal codes; results are the same bits as with int32
     column indices, and matrices with more than 256 diagonals keep int32."""
