@@ -134,6 +134,11 @@ int b200_sell_pack(int32_t m, const int32_t *h_ai, const int32_t *h_aj, const do
  * (a long row's pieces never straddle two blocks).  Sizes first, then the arrays.               */
 int b200_wmerge_plan_size(int32_t m, const int32_t *h_ai, int32_t *nchunks, int32_t *nblocks);
 int b200_wmerge_plan(int32_t m, const int32_t *h_ai, int32_t *chunks4, int32_t *blk);
+/* Column blocks of the skewed plan (x larger than 1.5 x limit_bytes: A = [A_0 | A_1 | ...], y = A_0 x,
+ * y += A_1 x, ...), host only: *nblocks (0 = no blocking) and, when split != NULL, for every block b
+ * and row r the first entry of row r that belongs to a later block: split[b * m + r].           */
+int b200_colblock_split(int32_t m, int32_t n, const int32_t *h_ai, const int32_t *h_aj,
+                        int64_t limit_bytes, int32_t *nblocks, int32_t *split);
 /* Device pointers of the mirrors (for tests / composition), any may be NULL.                 */
 int b200_csr_device_arrays(b200_csr_t A, const int32_t **d_ai, const int32_t **d_aj,
                            const double **d_aa);

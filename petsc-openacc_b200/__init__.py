@@ -81,7 +81,7 @@ ABI_SYMBOLS = [
     "b200_vec_pointwise_mult", "b200_vec_dot", "b200_vec_norm2", "b200_vec_norm_inf",
     "b200_vec_sum", "b200_cg_jacobi", "b200_gen_vector",
     "b200_csr_build_sell", "b200_sell_pack_size", "b200_sell_pack",
-    "b200_wmerge_plan_size", "b200_wmerge_plan",
+    "b200_wmerge_plan_size", "b200_wmerge_plan", "b200_colblock_split",
 ]
 
 
@@ -261,6 +261,19 @@ def wmerge_plan(ai):
     blk = np.zeros(nb.value + 1, np.int32)
     check(lib.b200_wmerge_plan(C.c_int32(m), _np_ptr(ai), _np_ptr(chunks), _np_ptr(blk)))
     return chunks[:nc.value], blk
+
+
+def colblock_split(ai, aj, n, limit_bytes):
+    """Host-only column-block split of the skewed plan: (nblocks, split[nblocks, m])."""
+    ai = np.ascontiguousarray(ai, dtype=np.int32)
+    aj = np.ascontiguousarray(aj, dtype=np.int32)
+    m = len(ai) - 1
+    nb = C.c_int32(0)
+    check(lib.b200_colblock_split(C.c_int32(m), C.c_int32(n), _np_ptr(ai), _np_ptr(aj), C.c_int64(limit_bytes), C.byref(nb), None))
+    split = np.zeros((max(nb.value, 1), max(m, 1)), np.int32)
+    if nb.value:
+        check(lib.b200_colblock_split(C.c_int32(m), C.c_int32(n), _np_ptr(ai), _np_ptr(aj), C.c_int64(limit_bytes), C.byref(nb), _np_ptr(split)))
+    return nb.value, split[:nb.value, :m]
 
 
 def gen_vector(n, seed=0xB200):

@@ -1340,6 +1340,38 @@ static void build_host_blocks(b200_csr_s *A, const int32_t *ai, const int32_t *a
 // plan, and y = A x becomes y = A_0 x, y += A_1 x, ... -- MatMultAdd continues the row sum from y, and
 // because columns ascend inside a row that is exactly the reference's left-to-right order: same bits.
 // An extra copy of aj/aa (like the explicit transpose); dropped by b200_csr_update_values.
+// number of column blocks for an x of n doubles (0: no blocking) and the first column past block b
+static int colblock_count(int64_t n, size_t limit)
+{
+  const size_t xbytes = (size_t)n * sizeof(double);
+  if (xbytes <= limit + limit / 2) return 0;                        // up to 1.5 blocks the one-pass kernel is as fast
+  return (int)((xbytes + limit - 1) / limit);
+}
+static int32_t colblock_end(int32_t n, int nb, int b) { return (b + 1 == nb) ? n : (int32_t)((long long)n * (b + 1) / nb); }
+
+// host only (for the CPU tests): how many blocks, and for every block the end of its part of every row --
+// split[b * m + r] = the first entry of row r that belongs to a later block (so block b holds
+// [split[(b-1) * m + r], split[b * m + r]) of row r, block 0 from ai[r])
+extern "C" int b200_colblock_split(int32_t m, int32_t n, const int32_t *h_ai, const int32_t *h_aj, int64_t limit_bytes,
+                                   int32_t *nblocks, int32_t *split)
+{
+  if (m < 0 || n < 0 || !h_ai || limit_bytes < 1 || !nblocks) return set_error(B200_ERR_ARG, "b200_colblock_split: bad argument");
+  const int nb = colblock_count(n, (size_t)limit_bytes);
+  *nblocks = nb;
+  if (!split || nb == 0) return B200_OK;
+  std::vector<int32_t> from(h_ai, h_ai + m);
+  for (int b = 0; b < nb; ++b) {
+    const int32_t cend = colblock_end(n, nb, b);
+    for (int r = 0; r < m; ++r) {
+      int32_t k = from[r];
+      while (k < h_ai[r + 1] && h_aj[k] < cend) ++k;
+      from[r] = k;
+      split[(size_t)b * m + r] = k;
+    }
+  }
+  return B200_OK;
+}
+
 static int alloc_mirrors(b200_csr_s *A);
 static int fill_ai_tail(b200_csr_s *A);
 static int build_colblocks(b200_csr_s *A, const int32_t *ai, const int32_t *aj, const double *aa)
@@ -1348,15 +1380,14 @@ static int build_colblocks(b200_csr_s *A, const int32_t *ai, const int32_t *aj, 
   // (B200_COLBLOCK_KB: the same limit in KB, so that the tests can block small matrices)
   const int    kb    = env_int("B200_COLBLOCK_KB", 0);
   const size_t limit = kb > 0 ? (size_t)kb << 10 : (size_t)std::max(1, env_int("B200_COLBLOCK_MB", 40)) << 20;
-  const size_t xbytes = (size_t)A->n * sizeof(double);
-  if (xbytes <= limit + limit / 2) return B200_OK;                  // up to 60 MB the one-pass kernel is as fast
-  const int nb = (int)((xbytes + limit - 1) / limit);
+  const int nb = colblock_count(A->n, limit);                       // 0 up to 60 MB of x: the one-pass kernel is as fast
+  if (nb == 0) return B200_OK;
   const int m = A->m;
   std::vector<int32_t> bi((size_t)m + 1), bj;
   std::vector<double>  ba;
   std::vector<int32_t> from(ai, ai + m);                            // next unread entry of every row
   for (int b = 0; b < nb; ++b) {
-    const int32_t cend = (b + 1 == nb) ? A->n : (int32_t)((long long)A->n * (b + 1) / nb);
+    const int32_t cend = colblock_end(A->n, nb, b);
     bj.clear(); ba.clear();
     bi[0] = 0;
     for (int r = 0; r < m; ++r) {

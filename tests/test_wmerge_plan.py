@@ -104,3 +104,31 @@ def test_invariants_for_arbitrary_row_lengths(pk, lens):
     ai = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     chunks, blk = pk.wmerge_plan(ai)
     check_invariants(ai, chunks, blk)
+
+
+def test_column_blocks_continue_every_row_left_to_right(pk):
+    """A = [A_0 | A_1 | ...]: no blocking up to 1.5 blocks of x; otherwise every row is cut at ascending
+    column bounds, the pieces are contiguous and in order, and summing them block after block -- each
+    block starting from the previous block's y, as MatMultAdd does -- gives the oracle's bits."""
+    ai, aj, aa = gen.powerlaw(3000, lmax=2000, seed=9)
+    n = 3000
+    assert pk.colblock_split(ai, aj, n, n * 8)[0] == 0 and pk.colblock_split(ai, aj, n, int(n * 8 / 1.5))[0] == 0
+    nb, split = pk.colblock_split(ai, aj, n, 4096)
+    assert nb == -(-n * 8 // 4096) and split.shape == (nb, 3000)
+    x = gen.uniform_pm1(n, 2)
+    y = np.zeros(3000)
+    lo = ai[:-1].astype(np.int64)
+    for b in range(nb):
+        hi = split[b].astype(np.int64)
+        assert np.all(hi >= lo) and np.all(hi <= ai[1:])
+        cend = n if b + 1 == nb else n * (b + 1) // nb
+        for r in range(3000):
+            seg = aj[lo[r]:hi[r]]
+            assert np.all(seg < cend) and (hi[r] == ai[r + 1] or aj[hi[r]] >= cend)
+            s = y[r]
+            for k in range(lo[r], hi[r]):
+                s = float(np.float64(s) + np.float64(aa[k]) * np.float64(x[aj[k]]))
+            y[r] = s
+        lo = hi
+    assert np.array_equal(lo, ai[1:])
+    assert np.array_equal(y, oracle.matmult(ai, aj, aa, x))
