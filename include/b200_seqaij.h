@@ -58,8 +58,9 @@ enum {
   B200_KERNEL_ROW    = 1,  /* thread per row straight from global memory (the reference's shape) */
   B200_KERNEL_STREAM = 2,  /* TMA-bulk-staged CSR tiles, thread per row out of shared memory     */
   B200_KERNEL_VECTOR = 3,  /* sub-warp per row, __shfl_xor reduction                             */
-  B200_KERNEL_MERGE  = 4,  /* skewed rows: nnz-balanced whole-row tiles + a warp per long row (exact
-                              order); B200_MERGE_SPLIT=1: split-row tiles with carry fix-up       */
+  B200_KERNEL_MERGE  = 4,  /* skewed rows: warp-granular chunks of <= 128 non-zeros, rows summed in CSR
+                              order (k_wmerge; in column blocks when x exceeds 60 MB);
+                              B200_MERGE_SPLIT=1 + MODE_FAST: split-row tiles with carry fix-up   */
   B200_KERNEL_CPROW  = 5,  /* compressed-row: only the non-empty rows                            */
   B200_KERNEL_SELL   = 6   /* the optional SELL-32-sigma copy (b200_csr_build_sell); never chosen by
                               AUTO                                                               */

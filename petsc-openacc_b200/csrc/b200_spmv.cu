@@ -1438,7 +1438,7 @@ extern "C" int b200_init(int device)
 extern "C" const char *b200_last_error(void) { return g_last_error.c_str(); }
 extern "C" uint64_t    b200_launch_count(void) { return g_launches.load(); }
 extern "C" int         b200_device_sm_count(void) { return ensure_device() ? 0 : sm_count(); }
-extern "C" const char *b200_version(void) { return "b200-seqaij 0.1 (sm_100a)"; }
+extern "C" const char *b200_version(void) { return "b200-seqaij 0.2 (sm_100a)"; }
 
 static int alloc_mirrors(b200_csr_s *A)
 {
